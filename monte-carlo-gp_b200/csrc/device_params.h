@@ -1,0 +1,43 @@
+// Device-side race parameter blocks, derived on the host from mcgp_race_params (include/mcgp.h).
+#pragma once
+#include <stdint.h>
+
+#define MCGP_LANES 32
+#define MCGP_NC 5
+
+// ---- native mode (FP32 / integer thresholds) -------------------------------------------------
+// Everything a warp needs for one race.  ~6.6 KB, staged once per block into shared memory; the
+// per-driver scalars then live in registers (lane == driver index) for the whole kernel.
+struct NativeRace {
+    int32_t n;            // drivers
+    int32_t total_laps;
+    int32_t track;        // 0 dry, 1 damp, 2 wet
+    int32_t pop_no_medium, pop_no_soft;
+    uint32_t stream;
+    int32_t grid_fixed;   // 1: grid_probs is a deterministic permutation, fixed_slot[] is the grid
+    int32_t _pad;
+    float pit_loss, ovt_delta, drs_delta, dirty_thr, dirty_pen;
+    uint32_t red_thr, sc_thr, vsc_thr;       // floor(p * 2^32), event iff word < thr
+    float pace[MCGP_LANES];                  // base_pace
+    float deg_ovt[MCGP_LANES];               // raw tire_deg (overtake pace, src/simulation.py:514)
+    float sigma[MCGP_LANES];                 // driver_variance
+    uint32_t dnf_thr[MCGP_LANES];            // per-lap DNF threshold, laps >= 2
+    uint32_t lap1_thr[MCGP_LANES];           // 4 x team rate, lap 1
+    float eff_deg[MCGP_NC][MCGP_LANES];      // compound_deg * (deg/0.05 if deg>0 else 1)   (:320-322)
+    float opt[MCGP_NC][MCGP_LANES];          // pit window per compound, 0.85/1.1 scaled+truncated (:455-462)
+    float cdelta[MCGP_NC];                   // compound pace delta (:325)
+    float grid[MCGP_LANES][MCGP_LANES];      // [pos][driver] qualifying probabilities
+    uint8_t fixed_slot[MCGP_LANES];          // grid_fixed: grid slot of each driver
+};
+
+// ---- replay mode (FP64, bit-exact) -----------------------------------------------------------
+struct ReplayRace {
+    int32_t n, total_laps, track, pop_no_medium, pop_no_soft, _pad;
+    double pit_loss, ovt_delta, sc_p, vsc_p, red_p, drs_delta, dirty_thr, dirty_pen;
+    double cdelta[MCGP_NC], cdeg[MCGP_NC];
+    double opt[MCGP_NC][MCGP_LANES];         // already scaled/truncated per driver
+    double pace[MCGP_LANES], deg[MCGP_LANES], sigma[MCGP_LANES];
+    double dnf_rate[MCGP_LANES], lap1_rate[MCGP_LANES];   // lap1_rate = team_rate * 4.0
+    double grid[MCGP_LANES][MCGP_LANES];     // [driver][pos]
+    uint8_t kind[MCGP_LANES][MCGP_LANES];    // MCGP_ITEM_*
+};

@@ -1,0 +1,339 @@
+// C ABI of libmcgp.so (declared in include/mcgp.h): context management, host-side derivation of the
+// device parameter blocks from mcgp_race_params, and the launches.  No torch types, no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/mcgp.h"
+#include "device_params.h"
+
+namespace mcgp {
+cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, unsigned long long n_sims,
+                          unsigned long long sim_begin, unsigned long long seed, bool exact,
+                          unsigned long long* hist, uint8_t* finish, float* times, int sm_count, cudaStream_t st);
+cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
+                          const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
+                          double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status, int sm_count,
+                          cudaStream_t st);
+}  // namespace mcgp
+
+struct mcgp_context {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    std::string err;
+    NativeRace* native_dev = nullptr;
+    ReplayRace* replay_dev = nullptr;
+    int n_races = 0, n_drivers = 0;
+    int launches = 0;
+    // grow-only scratch for the host-buffer entry points
+    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_sz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static std::string g_create_error;
+
+static int fail(mcgp_handle h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(h, MCGP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+static int scratch_get(mcgp_handle h, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (h->scratch_sz[slot] < bytes) {
+        if (h->scratch[slot]) cudaFree(h->scratch[slot]);
+        h->scratch[slot] = nullptr;
+        h->scratch_sz[slot] = 0;
+        cudaError_t e = cudaMalloc(&h->scratch[slot], bytes);
+        if (e != cudaSuccess) return fail(h, MCGP_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        h->scratch_sz[slot] = bytes;
+    }
+    *out = h->scratch[slot];
+    return MCGP_OK;
+}
+
+// ---- host-side parameter derivation ---------------------------------------------------------
+static uint32_t prob_threshold(double p) {  // event iff 32-bit word < threshold
+    if (!(p > 0.0)) return 0u;
+    if (p >= 1.0) return 0xffffffffu;
+    return (uint32_t)floor(p * 4294967296.0);
+}
+
+static int validate(mcgp_handle h, const mcgp_race_params* r) {
+    if (r->n_drivers < 1 || r->n_drivers > MCGP_MAX_DRIVERS) return fail(h, MCGP_EINVAL, "n_drivers must be in 1..32");
+    if (r->total_laps < 1 || r->total_laps > 65535) return fail(h, MCGP_EINVAL, "total_laps must be in 1..65535");
+    if (r->track_condition < 0 || r->track_condition > 2) return fail(h, MCGP_EINVAL, "bad track_condition");
+    if (!(r->pop_no_medium == MCGP_SOFT || r->pop_no_medium == MCGP_HARD)) return fail(h, MCGP_EINVAL, "pop_no_medium must be SOFT or HARD");
+    if (!(r->pop_no_soft == MCGP_MEDIUM || r->pop_no_soft == MCGP_HARD)) return fail(h, MCGP_EINVAL, "pop_no_soft must be MEDIUM or HARD");
+    for (int d = 0; d < r->n_drivers; d++)
+        for (int p = 0; p < r->n_drivers; p++) {
+            const double v = r->grid_probs[d][p];
+            if (v != v) return fail(h, MCGP_EINVAL, "probabilities contain NaN");              // np.random.choice's message
+            if (v < 0) return fail(h, MCGP_EINVAL, "probabilities are not non-negative");      // idem
+            if (r->grid_kind[d][p] > 2) return fail(h, MCGP_EINVAL, "bad grid_kind");
+        }
+    return MCGP_OK;
+}
+
+static double pit_window(const mcgp_race_params* r, int c, int d) {  // src/simulation.py:455-462
+    double optimal = r->compound_optimal_laps[c];
+    const double driver_deg = r->tire_deg_pit[d];
+    if (driver_deg > 0.05) optimal = trunc(optimal * 0.85);
+    else if (driver_deg < 0.02) optimal = trunc(optimal * 1.1);
+    return optimal;
+}
+
+static void derive_native(const mcgp_race_params* r, NativeRace* o) {
+    memset(o, 0, sizeof(*o));
+    const int n = r->n_drivers;
+    o->n = n; o->total_laps = r->total_laps; o->track = r->track_condition;
+    o->pop_no_medium = r->pop_no_medium; o->pop_no_soft = r->pop_no_soft; o->stream = r->stream;
+    o->pit_loss = (float)r->pit_loss; o->ovt_delta = (float)r->overtake_delta; o->drs_delta = (float)r->drs_delta;
+    o->dirty_thr = (float)r->dirty_air_threshold; o->dirty_pen = (float)r->dirty_air_penalty;
+    o->red_thr = prob_threshold(r->red_flag_probability);
+    o->sc_thr = prob_threshold(r->sc_probability);
+    o->vsc_thr = prob_threshold(r->vsc_probability);
+    for (int c = 0; c < MCGP_NC; c++) o->cdelta[c] = (float)r->compound_pace_delta[c];
+    for (int d = 0; d < MCGP_LANES; d++) {
+        const bool car = d < n;
+        o->pace[d] = car ? (float)r->base_pace[d] : 0.0f;
+        o->deg_ovt[d] = car ? (float)r->tire_deg[d] : 0.0f;
+        o->sigma[d] = car ? (float)r->driver_variance[d] : 0.0f;
+        o->dnf_thr[d] = car ? prob_threshold(r->dnf_rate[d]) : 0u;
+        o->lap1_thr[d] = car ? prob_threshold(r->team_dnf_rate[d] * 4.0) : 0u;  // LAP_1_DNF_MULTIPLIER :282
+        const double deg = car ? r->tire_deg[d] : 0.05;
+        const double driver_factor = deg > 0 ? deg / 0.05 : 1.0;  // :321
+        for (int c = 0; c < MCGP_NC; c++) {
+            o->eff_deg[c][d] = car ? (float)(r->compound_deg_rate[c] * driver_factor) : 0.0f;
+            o->opt[c][d] = car ? (float)pit_window(r, c, d) : 1e30f;
+        }
+    }
+    for (int p = 0; p < MCGP_LANES; p++)
+        for (int d = 0; d < MCGP_LANES; d++)
+            o->grid[p][d] = (p < n && d < n && r->grid_kind[d][p] != MCGP_ITEM_INT0) ? (float)r->grid_probs[d][p] : 0.0f;
+    // deterministic grid (one-hot rows forming a permutation, src/predictor.py:189-205): skip the sampler
+    bool fixed = true;
+    int col_owner[MCGP_LANES];
+    for (int p = 0; p < n && fixed; p++) {
+        int cnt = 0;
+        for (int d = 0; d < n; d++) if (o->grid[p][d] > 0.0f) { cnt++; col_owner[p] = d; }
+        if (cnt != 1) fixed = false;
+    }
+    if (fixed) {
+        int seen[MCGP_LANES] = {0};
+        for (int p = 0; p < n; p++) {
+            if (seen[col_owner[p]]++) { fixed = false; break; }
+        }
+        if (fixed) for (int p = 0; p < n; p++) o->fixed_slot[col_owner[p]] = (uint8_t)p;
+    }
+    o->grid_fixed = fixed ? 1 : 0;
+}
+
+static void derive_replay(const mcgp_race_params* r, ReplayRace* o) {
+    memset(o, 0, sizeof(*o));
+    const int n = r->n_drivers;
+    o->n = n; o->total_laps = r->total_laps; o->track = r->track_condition;
+    o->pop_no_medium = r->pop_no_medium; o->pop_no_soft = r->pop_no_soft;
+    o->pit_loss = r->pit_loss; o->ovt_delta = r->overtake_delta; o->sc_p = r->sc_probability;
+    o->vsc_p = r->vsc_probability; o->red_p = r->red_flag_probability; o->drs_delta = r->drs_delta;
+    o->dirty_thr = r->dirty_air_threshold; o->dirty_pen = r->dirty_air_penalty;
+    for (int c = 0; c < MCGP_NC; c++) { o->cdelta[c] = r->compound_pace_delta[c]; o->cdeg[c] = r->compound_deg_rate[c]; }
+    for (int d = 0; d < n; d++) {
+        o->pace[d] = r->base_pace[d]; o->deg[d] = r->tire_deg[d]; o->sigma[d] = r->driver_variance[d];
+        o->dnf_rate[d] = r->dnf_rate[d];
+        o->lap1_rate[d] = r->team_dnf_rate[d] * 4.0;  // base_dnf_rate * LAP_1_DNF_MULTIPLIER :287
+        for (int c = 0; c < MCGP_NC; c++) o->opt[c][d] = pit_window(r, c, d);
+        for (int p = 0; p < n; p++) { o->grid[d][p] = r->grid_probs[d][p]; o->kind[d][p] = r->grid_kind[d][p]; }
+    }
+}
+
+// ---- ABI ------------------------------------------------------------------------------------
+extern "C" {
+
+int mcgp_abi_version(void) { return MCGP_ABI_VERSION; }
+
+int mcgp_create(mcgp_handle* out, int device) {
+    mcgp_handle h = nullptr;
+    if (!out) return fail(nullptr, MCGP_EINVAL, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, MCGP_ENODEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                                 " (libmcgp has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(nullptr, MCGP_EINVAL, "device index out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, MCGP_ENODEVICE, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MCGP_ENODEVICE, "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                                 "; libmcgp is built for sm_100a (B200) only");
+    h = new (std::nothrow) mcgp_context();
+    if (!h) return fail(nullptr, MCGP_ENOMEM, "out of host memory");
+    h->device = device; h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete h; return fail(nullptr, MCGP_ENODEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+    *out = h;
+    return MCGP_OK;
+}
+
+int mcgp_destroy(mcgp_handle h) {
+    if (!h) return MCGP_OK;
+    cudaSetDevice(h->device);
+    if (h->native_dev) cudaFree(h->native_dev);
+    if (h->replay_dev) cudaFree(h->replay_dev);
+    for (int i = 0; i < 8; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
+    delete h;
+    return MCGP_OK;
+}
+
+const char* mcgp_last_error(mcgp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mcgp_device_info(mcgp_handle h, int* sm_count, int* sm_clock_khz, int* cc_major, int* cc_minor) {
+    if (!h) return MCGP_EINVAL;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    if (sm_count) *sm_count = h->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = khz;
+    if (cc_major) *cc_major = h->cc_major;
+    if (cc_minor) *cc_minor = h->cc_minor;
+    return MCGP_OK;
+}
+
+int mcgp_last_launch_count(mcgp_handle h) { return h ? h->launches : 0; }
+
+int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races) {
+    if (!h) return MCGP_EINVAL;
+    if (!races || n_races < 1) return fail(h, MCGP_EINVAL, "races is NULL or n_races < 1");
+    for (int r = 0; r < n_races; r++) {
+        int rc = validate(h, &races[r]);
+        if (rc) return rc;
+        if (races[r].n_drivers != races[0].n_drivers) return fail(h, MCGP_EINVAL, "all races of a batch must have the same n_drivers");
+    }
+    CU(cudaSetDevice(h->device));
+    NativeRace* nat = new (std::nothrow) NativeRace[n_races];
+    ReplayRace* rep = new (std::nothrow) ReplayRace[n_races];
+    if (!nat || !rep) { delete[] nat; delete[] rep; return fail(h, MCGP_ENOMEM, "out of host memory"); }
+    for (int r = 0; r < n_races; r++) { derive_native(&races[r], &nat[r]); derive_replay(&races[r], &rep[r]); }
+    if (h->native_dev) { cudaFree(h->native_dev); h->native_dev = nullptr; }
+    if (h->replay_dev) { cudaFree(h->replay_dev); h->replay_dev = nullptr; }
+    cudaError_t e = cudaMalloc(&h->native_dev, sizeof(NativeRace) * n_races);
+    if (e == cudaSuccess) e = cudaMalloc(&h->replay_dev, sizeof(ReplayRace) * n_races);
+    if (e == cudaSuccess) e = cudaMemcpy(h->native_dev, nat, sizeof(NativeRace) * n_races, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->replay_dev, rep, sizeof(ReplayRace) * n_races, cudaMemcpyHostToDevice);
+    delete[] nat; delete[] rep;
+    if (e != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("upload: ") + cudaGetErrorString(e));
+    h->n_races = n_races; h->n_drivers = races[0].n_drivers;
+    return MCGP_OK;
+}
+
+int mcgp_launch_native(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
+                       uint64_t* hist_dev, uint8_t* finish_dev, float* times_dev, void* cuda_stream) {
+    if (!h) return MCGP_EINVAL;
+    if (!h->native_dev) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
+    if (!hist_dev) return fail(h, MCGP_EINVAL, "hist_dev is NULL");
+    h->launches = 0;
+    if (n_sims == 0) return MCGP_OK;
+    CU(cudaSetDevice(h->device));
+    CU(mcgp::launch_native(h->native_dev, h->n_races, h->n_drivers, n_sims, sim_begin, seed, (flags & MCGP_F_EXACT_NORMAL) != 0,
+                           (unsigned long long*)hist_dev, finish_dev, times_dev, h->sm_count, (cudaStream_t)cuda_stream));
+    h->launches = 1;
+    return MCGP_OK;
+}
+
+int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims, uint64_t sim_begin,
+                    uint64_t seed, uint32_t flags, uint64_t* hist_host, uint8_t* finish_host) {
+    if (!h) return MCGP_EINVAL;
+    if (!hist_host) return fail(h, MCGP_EINVAL, "hist_host is NULL");
+    int rc = mcgp_upload_races(h, races, n_races);
+    if (rc) return rc;
+    const size_t n = (size_t)h->n_drivers;
+    const size_t hist_bytes = (size_t)n_races * n * n * sizeof(uint64_t);
+    const size_t fin_bytes = finish_host ? (size_t)n_races * n_sims * n : 0;
+    void *hist_dev = nullptr, *fin_dev = nullptr;
+    if ((rc = scratch_get(h, 0, hist_bytes, &hist_dev))) return rc;
+    if (finish_host && (rc = scratch_get(h, 1, fin_bytes, &fin_dev))) return rc;
+    CU(cudaMemcpy(hist_dev, hist_host, hist_bytes, cudaMemcpyHostToDevice));  // counts accumulate (+=)
+    rc = mcgp_launch_native(h, n_sims, sim_begin, seed, flags, (uint64_t*)hist_dev, (uint8_t*)fin_dev, nullptr, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpy(hist_host, hist_dev, hist_bytes, cudaMemcpyDeviceToHost));
+    if (finish_host && fin_bytes) CU(cudaMemcpy(finish_host, fin_dev, fin_bytes, cudaMemcpyDeviceToHost));
+    CU(cudaDeviceSynchronize());
+    return MCGP_OK;
+}
+
+int mcgp_launch_replay(mcgp_handle h, uint64_t n_sims, const double* u_py_dev, const double* z_dev, const double* u_np_dev,
+                       const int64_t* off_dev, uint64_t* hist_dev, uint8_t* finish_dev, double* times_dev,
+                       int16_t* dnf_lap_dev, uint8_t* grid_dev, int64_t* used_dev, int32_t* status_dev, void* cuda_stream) {
+    if (!h) return MCGP_EINVAL;
+    if (!h->replay_dev) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
+    if (h->n_races != 1) return fail(h, MCGP_EINVAL, "replay mode takes exactly one race");
+    if (!hist_dev || !off_dev || !u_py_dev || !z_dev || !u_np_dev) return fail(h, MCGP_EINVAL, "NULL tape/hist pointer");
+    h->launches = 0;
+    if (n_sims == 0) return MCGP_OK;
+    CU(cudaSetDevice(h->device));
+    CU(mcgp::launch_replay(h->replay_dev, n_sims, u_py_dev, z_dev, u_np_dev, (const long long*)off_dev,
+                           (unsigned long long*)hist_dev, finish_dev, times_dev, dnf_lap_dev, grid_dev,
+                           (long long*)used_dev, status_dev, h->sm_count, (cudaStream_t)cuda_stream));
+    h->launches = 1;
+    return MCGP_OK;
+}
+
+int mcgp_run_replay(mcgp_handle h, const mcgp_race_params* race, uint64_t n_sims, const double* u_py, const double* z,
+                    const double* u_np, const int64_t* off, uint64_t* hist_host, uint8_t* finish_host, double* times_host,
+                    int16_t* dnf_lap_host, uint8_t* grid_host, int64_t* used_host) {
+    if (!h) return MCGP_EINVAL;
+    if (!race || !off || !hist_host) return fail(h, MCGP_EINVAL, "NULL argument");
+    int rc = mcgp_upload_races(h, race, 1);
+    if (rc) return rc;
+    const size_t n = (size_t)h->n_drivers;
+    const int64_t* end = off + 3 * n_sims;
+    const size_t b_py = (size_t)end[0] * 8, b_z = (size_t)end[1] * 8, b_np = (size_t)end[2] * 8;
+    if ((b_py && !u_py) || (b_z && !z) || (b_np && !u_np)) return fail(h, MCGP_EINVAL, "NULL tape");
+    const size_t b_off = (size_t)(3 * (n_sims + 1)) * 8, b_hist = n * n * 8;
+    void *d_py, *d_z, *d_np, *d_off, *d_hist, *d_out, *d_status;
+    if ((rc = scratch_get(h, 2, b_py, &d_py)) || (rc = scratch_get(h, 3, b_z, &d_z)) || (rc = scratch_get(h, 4, b_np, &d_np)) ||
+        (rc = scratch_get(h, 5, b_off, &d_off)) || (rc = scratch_get(h, 0, b_hist, &d_hist)) || (rc = scratch_get(h, 7, 16, &d_status)))
+        return rc;
+    // per-sim outputs packed into one scratch buffer: times | used | dnf_lap | finish | grid
+    const size_t o_times = 0, o_used = o_times + n_sims * n * 8, o_dnf = o_used + n_sims * 3 * 8;
+    const size_t o_fin = o_dnf + ((n_sims * n * 2 + 7) & ~(size_t)7), o_grid = o_fin + ((n_sims * n + 7) & ~(size_t)7);
+    const size_t b_out = o_grid + n_sims * n;
+    if ((rc = scratch_get(h, 6, b_out, &d_out))) return rc;
+    char* ob = (char*)d_out;
+    if (b_py) CU(cudaMemcpy(d_py, u_py, b_py, cudaMemcpyHostToDevice));
+    if (b_z) CU(cudaMemcpy(d_z, z, b_z, cudaMemcpyHostToDevice));
+    if (b_np) CU(cudaMemcpy(d_np, u_np, b_np, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_off, off, b_off, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_hist, hist_host, b_hist, cudaMemcpyHostToDevice));
+    CU(cudaMemset(d_status, 0, 16));
+    rc = mcgp_launch_replay(h, n_sims, (const double*)d_py, (const double*)d_z, (const double*)d_np, (const int64_t*)d_off,
+                            (uint64_t*)d_hist, finish_host ? (uint8_t*)(ob + o_fin) : nullptr,
+                            times_host ? (double*)(ob + o_times) : nullptr, dnf_lap_host ? (int16_t*)(ob + o_dnf) : nullptr,
+                            grid_host ? (uint8_t*)(ob + o_grid) : nullptr, used_host ? (int64_t*)(ob + o_used) : nullptr,
+                            (int32_t*)d_status, nullptr);
+    if (rc) return rc;
+    int32_t status = 0;
+    CU(cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hist_host, d_hist, b_hist, cudaMemcpyDeviceToHost));
+    if (finish_host) CU(cudaMemcpy(finish_host, ob + o_fin, n_sims * n, cudaMemcpyDeviceToHost));
+    if (times_host) CU(cudaMemcpy(times_host, ob + o_times, n_sims * n * 8, cudaMemcpyDeviceToHost));
+    if (dnf_lap_host) CU(cudaMemcpy(dnf_lap_host, ob + o_dnf, n_sims * n * 2, cudaMemcpyDeviceToHost));
+    if (grid_host) CU(cudaMemcpy(grid_host, ob + o_grid, n_sims * n, cudaMemcpyDeviceToHost));
+    if (used_host) CU(cudaMemcpy(used_host, ob + o_used, n_sims * 3 * 8, cudaMemcpyDeviceToHost));
+    CU(cudaDeviceSynchronize());
+    if (status) return fail(h, MCGP_ETAPE, "a simulated race ran past the end of its tape");
+    return MCGP_OK;
+}
+
+}  // extern "C"

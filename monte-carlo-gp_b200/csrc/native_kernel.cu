@@ -1,0 +1,392 @@
+// Native-mode race kernel for sm_100a: one warp per simulated race, one lane per driver.
+//
+// Behavioural source: reference src/simulation.py:59-560 (run_monte_carlo / simulate_race and the
+// handlers; each step below cites its lines).  What is B200-native here and absent upstream:
+//   * lane == driver index, so every per-driver parameter sits in a register for the whole launch;
+//   * draws come from Philox4x32-10 keyed by (seed; sim, lap, lane, stream): any sim range can be
+//     launched on any GPU in any order and gives the same counts;
+//   * race times are FP32 *relative to the current leader* (re-based every lap in
+//     update_positions), which keeps ~1e-5 s resolution where absolute FP32 time would have 5e-4 s;
+//   * ordering = rank-by-counting over keys staged in shared memory (LDS.128 broadcast reads) plus
+//     an inverse permutation, so "car ahead" look-ups are single shuffles;
+//   * overtakes: pair conditions and draws are evaluated in parallel in rank space, the sequential
+//     time re-write chain of :522-531 collapses to a closed form over runs of consecutive successes
+//     (one REDUX.OR ballot + bit scans);
+//   * the finish-position histogram accumulates in shared memory (uint32) and is flushed once per
+//     block with 64-bit global atomics.
+// The scalar CPU mirror of exactly this algorithm is oracle/native_mirror.c (test infrastructure).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_params.h"
+#include "native_math.cuh"
+
+namespace mcgp {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+// VSC tyre-age rollback probability 0.3 (src/simulation.py:392) as a 32-bit threshold
+constexpr uint32_t kVscRollThr = 1288490188u;  // floor(0.3 * 2^32)
+
+__device__ __forceinline__ uint32_t time_key(float t) {
+    // order-preserving float -> uint32 map (negative times belong to retired cars)
+    uint32_t b = __float_as_uint(t);
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+
+// Rank of this lane's key among the n cars, ties broken by lane.  S_key: 32 words of warp scratch.
+template <int NV4>
+__device__ __forceinline__ int rank_by_count(uint32_t key, uint32_t* S_key, int lane, int n, uint32_t nmask) {
+    S_key[lane] = key;
+    __syncwarp();
+    int cnt = 0;
+    const uint4* v4 = reinterpret_cast<const uint4*>(S_key);
+#pragma unroll
+    for (int q = 0; q < NV4; q++) {
+        uint4 v = v4[q];
+        cnt += (v.x < key) ? 1 : 0;
+        cnt += (v.y < key) ? 1 : 0;
+        cnt += (v.z < key) ? 1 : 0;
+        cnt += (v.w < key) ? 1 : 0;
+    }
+    // exact ties are measure-zero events; detect them by a hole in the rank set and fix up
+    uint32_t seen = __reduce_or_sync(FULL, lane < n ? (1u << cnt) : 0u);
+    if (seen != nmask) {
+        for (int j = 0; j < lane; j++) cnt += (S_key[j] == key) ? 1 : 0;
+    }
+    __syncwarp();
+    return cnt;
+}
+
+struct Tables {  // per-lane view of the compound tables in shared memory
+    const NativeRace* R;
+    int lane;
+    __device__ __forceinline__ void load(int comp, float pace, float& eff, float& opt, float& pc) const {
+        eff = R->eff_deg[comp][lane];
+        opt = R->opt[comp][lane];
+        pc = __fadd_rn(pace, R->cdelta[comp]);
+    }
+};
+
+template <int NV4, bool kExact, bool kDetail>
+__global__ void __launch_bounds__(kThreads, 4)
+native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_sims, unsigned long long sim_begin,
+                   uint32_t seed_lo, uint32_t seed_hi, unsigned long long* __restrict__ hist,
+                   uint8_t* __restrict__ finish, float* __restrict__ times) {
+    __shared__ NativeRace R;
+    __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
+    __shared__ __align__(16) uint32_t S_key_all[kWarpsPerBlock][32];
+    __shared__ uint32_t S_inv_all[kWarpsPerBlock][32];
+
+    const int race = blockIdx.y;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(races + race);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&R);
+        for (int i = threadIdx.x; i < (int)(sizeof(NativeRace) / 4); i += kThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < MCGP_LANES * MCGP_LANES; i += kThreads) hist_s[i] = 0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* S_key = S_key_all[warp];
+    uint32_t* S_inv = S_inv_all[warp];
+    const int n = R.n, L = R.total_laps, track = R.track;
+    const uint32_t nmask = n >= 32 ? FULL : ((1u << n) - 1u);
+    const bool is_car = lane < n;
+    const float pace = R.pace[lane], deg_ovt = R.deg_ovt[lane], sigma = R.sigma[lane];
+    const uint32_t dnf_thr = R.dnf_thr[lane], lap1_thr = R.lap1_thr[lane];
+    const float pit_loss = R.pit_loss, ovt_delta = R.ovt_delta, drs_delta = R.drs_delta;
+    const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
+    const uint32_t red_thr = R.red_thr, sc_thr = R.sc_thr, vsc_thr = R.vsc_thr, stream = R.stream;
+    const Tables tab{&R, lane};
+
+    const unsigned long long warps_per_race = (unsigned long long)gridDim.x * kWarpsPerBlock;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * kWarpsPerBlock + warp; s < n_sims; s += warps_per_race) {
+        const unsigned long long sim = sim_begin + s;
+        const uint32_t sim_lo = (uint32_t)sim, sim_hi = (uint32_t)(sim >> 32);
+
+        // ---- _sample_grid (src/simulation.py:102-145): sequential draw without replacement -------
+        int slot = 0;
+        if (R.grid_fixed) {
+            slot = R.fixed_slot[lane];
+        } else {
+            const uint4 wg = philox4x32_10(sim_lo, sim_hi, (uint32_t)lane, stream, seed_lo, seed_hi);
+            bool remaining = is_car;
+            for (int pos = 0; pos < n; pos++) {
+                float p = remaining ? R.grid[pos][lane] : 0.0f;
+                float c = p;  // inclusive Hillis-Steele scan over lanes (the mirror replays this exact tree)
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    float v = __shfl_up_sync(FULL, c, d);
+                    if (lane >= d) c = __fadd_rn(c, v);
+                }
+                const float total = __shfl_sync(FULL, c, 31);
+                const float u = __fmul_rn((float)(__shfl_sync(FULL, wg.x, pos) >> 8), 5.9604644775390625e-08f);
+                const uint32_t rem_mask = __ballot_sync(FULL, remaining);
+                int sel;
+                if (total > 0.0f) {  // :125-126 (+ np.random.choice :137)
+                    const float target = __fmul_rn(u, total);
+                    const uint32_t m = __ballot_sync(FULL, remaining && p > 0.0f && c > target);
+                    sel = m ? (__ffs(m) - 1) : (31 - __clz(rem_mask));
+                } else {  // :127-130 uniform over the remaining drivers
+                    const int nrem = __popc(rem_mask);
+                    int k = (int)__fmul_rn(u, (float)nrem);
+                    k = k < nrem - 1 ? k : nrem - 1;
+                    uint32_t m = rem_mask;
+                    for (int i = 0; i < k; i++) m &= m - 1;
+                    sel = __ffs(m) - 1;
+                }
+                if (lane == sel) { slot = pos; remaining = false; }
+            }
+        }
+
+        // ---- _initialize_cars (:244-273) -------------------------------------------------------
+        int comp;
+        float age;
+        if (track == 2) { comp = 4; age = 0.0f; }
+        else if (track == 1) { comp = 3; age = 0.0f; }
+        else { comp = slot < 10 ? 0 : 1; age = slot < 10 ? 4.0f : 0.0f; }
+        uint32_t used = 1u << comp;
+        float eff, opt, pc;
+        tab.load(comp, pace, eff, opt, pc);
+
+        // ---- _simulate_lap_1 (:275-311) --------------------------------------------------------
+        bool dnf;
+        int dnf_lap = 0;
+        float t, last = 0.0f, ahead_last = 0.0f;
+        bool drs = false;
+        int pos_live = 0;
+        {
+            const uint4 w = philox4x32_10(sim_lo, sim_hi, (1u << 8) | (uint32_t)lane, stream, seed_lo, seed_hi);
+            dnf = !is_car || (w.x < lap1_thr);
+            if (is_car && dnf) dnf_lap = 1;
+            float z1, z2;
+            if (kExact) exact_normal2(w.y, w.z, z1, z2); else fast_normal2(w.y, w.z, z1, z2);
+            float x = __fmaf_rn(age, eff, pc);
+            x = __fmaf_rn(sigma, z1, x);
+            const float pf = fminf(1.5f, __fmaf_rn(0.1f, (float)(slot + 1), 0.5f));
+            float sd = __fmul_rn(pf, z2);
+            if (slot < 3) sd = fminf(sd, 1.0f);
+            const float lt = __fmaf_rn(-0.5f, sd, x);
+            t = dnf ? -(float)(lane + 1) : lt;  // retired on lap 1: distinct sentinel times below every runner
+            age = __fadd_rn(age, 1.0f);
+        }
+
+        int drs_until = 0;
+        int rank = 0;
+        bool need_rank = true;
+
+        for (int lap = 1; lap <= L; lap++) {
+            if (lap >= 2) {
+                const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, seed_lo, seed_hi);
+                // ---- race-interrupting events (:168-176), decided on lane 31's words ------------
+                int ev;
+                {
+                    uint4 we = w;
+                    if (n == 32) we = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 32u, stream, seed_lo, seed_hi);
+                    int code = (we.x < red_thr) ? 1 : (we.y < sc_thr) ? 2 : (we.z < vsc_thr) ? ((we.w < kVscRollThr) ? 4 : 3) : 0;
+                    ev = __shfl_sync(FULL, code, 31);
+                }
+                const int rem = L - lap;
+                const int nc_rule = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
+                if (ev) {
+                    if (ev == 1) {  // _handle_red_flag :397-431
+                        if (!dnf) {
+                            t = __fmul_rn(0.1f, (float)pos_live);
+                            age = 0.0f;
+                            comp = nc_rule;
+                            used |= 1u << comp;
+                            tab.load(comp, pace, eff, opt, pc);
+                        }
+                        drs_until = lap + 2;
+                    } else if (ev == 2) {  // _handle_safety_car :334-376
+                        if (!dnf) {
+                            t = __fmul_rn(0.5f, (float)pos_live);
+                            age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
+                        }
+                        drs_until = lap + 2;
+                    } else {  // _handle_vsc :378-395
+                        if (!dnf) {
+                            t = __fmul_rn(t, 0.8f);
+                            if (ev == 4) age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
+                        }
+                        drs_until = lap + 1;
+                    }
+                }
+
+                // ---- per-car lap (:186-223) ----------------------------------------------------
+                const bool was_live = !dnf;
+                if (was_live && w.x < dnf_thr) { dnf = true; dnf_lap = lap; }
+                float z, zunused;
+                if (kExact) exact_normal2(w.y, w.z, z, zunused); else z = fast_normal(w.y, w.z);
+                // _calculate_lap_time :313-332 (fuel is lap-uniform: every runner burns 1.5 kg per lap)
+                const float fuel_eff = __fmul_rn(fminf(110.0f, __fmul_rn(1.5f, (float)(lap - 1))), 0.03f);
+                const float fd = drs ? __fadd_rn(fuel_eff, drs_delta) : fuel_eff;
+                float x = __fmaf_rn(age, eff, pc);
+                x = __fadd_rn(x, -fd);
+                const float clean = __fmaf_rn(sigma, z, x);
+                float lt = clean;
+                if (t > 0.0f && ahead_last > 0.0f && t < dirty_thr)  // dirty air :208-216 (gap to the LEADER, Q3)
+                    lt = fmaxf(__fadd_rn(clean, dirty_pen), ahead_last);
+                if (!dnf) {
+                    t = __fadd_rn(t, lt);
+                    last = lt;
+                    age = __fadd_rn(age, 1.0f);
+                }
+
+                // ---- _handle_pit_stops (:433-494) ----------------------------------------------
+                const bool pit = !dnf && rem > 5 && age > opt;
+                if (__any_sync(FULL, pit)) {
+                    if (pit) {
+                        t = __fadd_rn(t, pit_loss);
+                        int nc = nc_rule;
+                        const uint32_t ud = used & 7u;
+                        if (track == 0 && __popc(ud) == 1 && ((ud >> nc) & 1u)) {  // two-compound rule :481-488
+                            const uint32_t avail = 7u & ~ud;
+                            if (rem > 20) nc = (avail & 2u) ? 1 : R.pop_no_medium;
+                            else nc = (avail & 1u) ? 0 : R.pop_no_soft;
+                        }
+                        comp = nc;
+                        used |= 1u << comp;
+                        age = 0.0f;
+                        tab.load(comp, pace, eff, opt, pc);
+                    }
+                }
+
+                // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
+                const float op = dnf ? __int_as_float(0x7fc00000) : __fmaf_rn(age, deg_ovt, pace);  // NaN blocks the pair (Q5)
+                const uint32_t u3 = ((w.y & 0xffu) << 8) | (w.z & 0xffu);
+                need_rank = true;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; pass++) {
+                    rank = rank_by_count<NV4>(is_car ? time_key(t) : 0xffffffffu, S_key, lane, n, nmask);
+                    if (is_car) S_inv[rank] = lane;
+                    __syncwarp();
+                    need_rank = false;
+                    const int la = (is_car && rank > 0) ? (int)S_inv[rank - 1] : lane;
+                    const float op_a = __shfl_sync(FULL, op, la);
+                    float delta = __fadd_rn(op_a, -op);
+                    if (drs) delta = __fadd_rn(delta, drs_delta);
+                    const uint32_t u16 = pass == 0 ? (w.w & 0xffffu) : pass == 1 ? (w.w >> 16) : u3;
+                    const float u = __fmul_rn((float)u16, 1.52587890625e-05f);
+                    const float prob = fminf(0.5f, __fmul_rn(delta, 0.5f));
+                    const bool succ = is_car && rank > 0 && delta > ovt_delta && u < prob;
+                    const uint32_t M = __reduce_or_sync(FULL, succ ? (1u << rank) : 0u);
+                    if (M == 0u) break;
+                    // closed form of the sequential re-write chain :522-531 over runs of successes
+                    const uint32_t clear_below = ~M & ((2u << rank) - 1u);
+                    const int j = 31 - __clz(clear_below);  // run start (bit 0 of M is never set)
+                    const int k = rank - j;
+                    const int lj = is_car ? (int)S_inv[j] : lane;
+                    const float base = __shfl_sync(FULL, t, lj);
+                    const int sn = (int)(((M >> rank) >> 1) & 1u);
+                    if (is_car && (k + sn) > 0) {
+                        float v = __fmaf_rn(-0.1f, (float)(k + sn), base);
+                        if (sn) v = __fadd_rn(v, 0.3f);
+                        t = v;
+                    }
+                    __syncwarp();
+                    need_rank = true;
+                }
+            }
+
+            // ---- _update_positions (:538-560), plus re-basing on the leader -----------------------
+            if (need_rank) {
+                rank = rank_by_count<NV4>(is_car ? time_key(t) : 0xffffffffu, S_key, lane, n, nmask);
+                if (is_car) S_inv[rank] = lane;
+                __syncwarp();
+            }
+            {
+                const bool live = !dnf;
+                const uint32_t LM = __reduce_or_sync(FULL, live ? (1u << rank) : 0u);
+                if (LM) {
+                    const int lead_lane = (int)S_inv[__ffs(LM) - 1];
+                    const float tl = __shfl_sync(FULL, t, lead_lane);
+                    const uint32_t below = live ? (LM & ((1u << rank) - 1u)) : 0u;
+                    const bool has_pred = below != 0u;
+                    const int pl = has_pred ? (int)S_inv[31 - __clz(below)] : lane;
+                    const float t_pred = __shfl_sync(FULL, t, pl);
+                    const float last_pred = __shfl_sync(FULL, last, pl);
+                    pos_live = __popc(below);
+                    const bool drs_on = lap > 2 && lap > drs_until;
+                    if (live) {
+                        drs = has_pred && drs_on && (__fadd_rn(t, -t_pred) < 1.0f);
+                        ahead_last = has_pred ? last_pred : 0.0f;
+                    }
+                    if (is_car) t = __fadd_rn(t, -tl);
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- final classification (:231-242) -----------------------------------------------------
+        {
+            const bool live = !dnf;
+            const int n_live = __popc(__ballot_sync(FULL, live));
+            // retired cars: later lap first, then larger time, then grid order (stable sort, reverse=True)
+            const float tc = dnf_lap == 1 ? 0.0f : t;
+            int worse = 0;
+            for (int j = 0; j < n; j++) {
+                const int jl = __shfl_sync(FULL, dnf_lap, j);
+                const float jt = __shfl_sync(FULL, tc, j);
+                const int js = __shfl_sync(FULL, slot, j);
+                const bool jd = __shfl_sync(FULL, (int)dnf, j) != 0;
+                const bool ahead = jd && j != lane &&
+                                   (jl > dnf_lap || (jl == dnf_lap && (jt > tc || (jt == tc && js < slot))));
+                worse += ahead ? 1 : 0;
+            }
+            const int pos = live ? pos_live : n_live + worse;
+            if (is_car) {
+                atomicAdd(&hist_s[lane * n + pos], 1u);
+                if (kDetail) {
+                    const unsigned long long o = ((unsigned long long)race * n_sims + s) * (unsigned long long)n;
+                    if (finish) finish[o + pos] = (uint8_t)lane;
+                    if (times) times[o + lane] = t;
+                }
+            }
+        }
+    }
+
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * n; i += kThreads) {
+        const uint32_t v = hist_s[i];
+        if (v) atomicAdd(&hist[(unsigned long long)race * n * n + i], (unsigned long long)v);
+    }
+}
+
+// ---- host-side launcher ------------------------------------------------------------------------
+template <int NV4>
+static cudaError_t launch_nv4(const NativeRace* races_dev, int n_races, unsigned long long n_sims,
+                              unsigned long long sim_begin, unsigned long long seed, bool exact, bool detail,
+                              unsigned long long* hist, uint8_t* finish, float* times, int blocks_per_race,
+                              cudaStream_t st) {
+    dim3 grid(blocks_per_race, n_races), block(kThreads);
+    const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+    if (exact) {
+        if (detail) native_race_kernel<NV4, true, true><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, lo, hi, hist, finish, times);
+        else native_race_kernel<NV4, true, false><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, lo, hi, hist, finish, times);
+    } else {
+        if (detail) native_race_kernel<NV4, false, true><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, lo, hi, hist, finish, times);
+        else native_race_kernel<NV4, false, false><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, lo, hi, hist, finish, times);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, unsigned long long n_sims,
+                          unsigned long long sim_begin, unsigned long long seed, bool exact,
+                          unsigned long long* hist, uint8_t* finish, float* times, int sm_count, cudaStream_t st) {
+    const bool detail = finish != nullptr || times != nullptr;
+    // persistent-style grid: 4 resident blocks per SM, split evenly over the races of the batch
+    const long long resident = (long long)sm_count * 4;
+    long long bpr = (resident + n_races - 1) / n_races;
+    const long long need = (long long)((n_sims + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    if (bpr > need) bpr = need;
+    if (bpr < 1) bpr = 1;
+    if (max_n <= 20)
+        return launch_nv4<5>(races_dev, n_races, n_sims, sim_begin, seed, exact, detail, hist, finish, times, (int)bpr, st);
+    return launch_nv4<8>(races_dev, n_races, n_sims, sim_begin, seed, exact, detail, hist, finish, times, (int)bpr, st);
+}
+
+}  // namespace mcgp

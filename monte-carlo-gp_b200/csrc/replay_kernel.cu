@@ -1,0 +1,423 @@
+// Replay-mode race kernel for sm_100a: FP64, one warp per simulated race, one lane per GRID SLOT.
+//
+// Consumes the reference's own random draws (three per-sim tapes: U_py = random.random(), Z = standard
+// normals behind np.random.normal, U_np = the uniform behind np.random.choice) in exactly the order
+// reference src/simulation.py consumes them (SURVEY.md §8 "Draw-order specification"), and evaluates
+// every expression in IEEE double with the reference's operation order.  This translation unit is
+// compiled with -fmad=false: no FMA contraction anywhere, so finishing orders AND race times are
+// bit-identical to CPython's.  lane == grid slot makes every "for car in cars" loop of the reference
+// (grid order) a lane-ordered prefix count (ballot + popc) over the tape cursors, and makes
+// the reference's stable-sort tie-break (list order) a plain (time, lane) comparison.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_params.h"
+
+namespace mcgp {
+
+constexpr int kRWarps = 4;
+constexpr int kRThreads = kRWarps * 32;
+constexpr unsigned RFULL = 0xffffffffu;
+
+struct Tape {
+    const double* p;
+    long long i, e;
+    __device__ __forceinline__ double at(long long k, int& err) const {
+        const long long q = i + k;
+        if (q < e) return p[q];
+        err = 1;
+        return 0.5;
+    }
+};
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(RFULL, v, src); }
+
+// rank of (v, lane) among lanes selected by `in_set` (warp-uniform mask), ascending, ties by lane
+__device__ __forceinline__ int rank_set(double v, uint32_t in_set, int lane) {
+    int cnt = 0;
+    uint32_t m = in_set;
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const double vj = shfl_d(v, j);
+        cnt += (vj < v || (vj == v && j < lane)) ? 1 : 0;
+    }
+    return cnt;
+}
+
+// CPython 3.12 builtin sum() over items P[0..n) with kinds K[0..n)  (executed uniformly by all lanes)
+__device__ double py_sum(const double* P, const uint8_t* K, int n, int& result_kind) {
+    int i = 0;
+    while (i < n && K[i] == 0) i++;
+    if (i == n) { result_kind = 0; return 0.0; }
+    double r = 0.0 + P[i];
+    int k = K[i];
+    i++;
+    if (k == 1) {
+        double c = 0.0;
+        bool fell_out = false;
+        for (; i < n; i++) {
+            if (K[i] == 1) {  // Neumaier
+                const double x = P[i];
+                const double t = r + x;
+                if (fabs(r) >= fabs(x)) c += (r - t) + x; else c += (x - t) + r;
+                r = t;
+            } else if (K[i] == 0) {
+                r += 0.0;
+            } else {
+                if (c != 0.0 && isfinite(c)) r += c;
+                r = r + P[i];
+                i++;
+                fell_out = true;
+                break;
+            }
+        }
+        if (!fell_out) {
+            if (c != 0.0 && isfinite(c)) r += c;
+            result_kind = 1;
+            return r;
+        }
+    }
+    for (; i < n; i++) r = r + (K[i] == 0 ? 0.0 : P[i]);
+    result_kind = 2;
+    return r;
+}
+
+__global__ void __launch_bounds__(kRThreads)
+replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sims, const double* __restrict__ u_py,
+                   const double* __restrict__ zt, const double* __restrict__ u_np, const long long* __restrict__ off,
+                   unsigned long long* __restrict__ hist, uint8_t* __restrict__ finish, double* __restrict__ times,
+                   int16_t* __restrict__ dnf_lap_out, uint8_t* __restrict__ grid_out, long long* __restrict__ used_out,
+                   int* __restrict__ status) {
+    __shared__ ReplayRace R;
+    __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
+    __shared__ double S_p_all[kRWarps][32];
+    __shared__ uint8_t S_k_all[kRWarps][32];
+    __shared__ uint32_t S_inv_all[kRWarps][32];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(race);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&R);
+        for (int i = threadIdx.x; i < (int)(sizeof(ReplayRace) / 4); i += kRThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < MCGP_LANES * MCGP_LANES; i += kRThreads) hist_s[i] = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* S_p = S_p_all[warp];
+    uint8_t* S_k = S_k_all[warp];
+    uint32_t* S_inv = S_inv_all[warp];
+    const int n = R.n, L = R.total_laps, track = R.track;
+    const bool is_car = lane < n;
+    const uint32_t nmask = n >= 32 ? RFULL : ((1u << n) - 1u);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int err = 0;
+
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * kRWarps;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * kRWarps + warp; s < n_sims; s += total_warps) {
+        Tape py{u_py, off[3 * s], off[3 * s + 3]};
+        Tape zz{zt, off[3 * s + 1], off[3 * s + 4]};
+        Tape np{u_np, off[3 * s + 2], off[3 * s + 5]};
+        const long long py0 = py.i, z0 = zz.i, np0 = np.i;
+
+        // ---- _sample_grid (src/simulation.py:102-145) + RandomState.choice restated -------------
+        int drv = 0;
+        {
+            uint32_t remaining = nmask;  // by driver index
+            for (int pos = 0; pos < n; pos++) {
+                // lane d prepares driver d's item :119-122
+                uint8_t kd = 0;
+                double pd = 0.0;
+                if (is_car && ((remaining >> lane) & 1u) && R.kind[lane][pos] != 0) { pd = R.grid[lane][pos]; kd = R.kind[lane][pos]; }
+                S_p[lane] = pd; S_k[lane] = kd;
+                __syncwarp();
+                int tk;
+                const double total = py_sum(S_p, S_k, n, tk);  // :123
+                __syncwarp();
+                if (total > 0) {  // :125-126
+                    pd = pd / total;
+                    kd = (tk == 2 || kd == 2) ? 2 : 1;
+                } else {  // :127-130
+                    const int n_rem = __popc(remaining);
+                    if ((remaining >> lane) & 1u) { pd = 1.0 / (double)n_rem; kd = 1; } else { pd = 0.0; kd = 0; }
+                }
+                S_p[lane] = pd; S_k[lane] = kd;
+                __syncwarp();
+                const double prob_sum = py_sum(S_p, S_k, n, tk);  // :133
+                __syncwarp();
+                if (prob_sum > 0 && fabs(prob_sum - 1.0) > 1e-9) pd = pd / prob_sum;  // :134-135
+                S_p[lane] = pd;
+                __syncwarp();
+                // p.cumsum(); cdf /= cdf[-1]; searchsorted(u, side='right')
+                double acc = S_p[0], mine = acc;
+                for (int d = 1; d < n; d++) { acc = acc + S_p[d]; if (d == lane) mine = acc; }
+                __syncwarp();
+                const double cdf = mine / acc;
+                const double u = np.at(0, err); np.i++;
+                int sel = __popc(__ballot_sync(RFULL, is_car && cdf <= u));
+                if (sel > n - 1) sel = n - 1;
+                if (lane == pos) drv = sel;
+                remaining &= ~(1u << sel);  // :139
+            }
+        }
+
+        // per-sim driver parameters (lane == grid slot, so they are looked up by the sampled driver)
+        const double pace = R.pace[drv], deg = R.deg[drv], sigma = R.sigma[drv];
+        const double dnf_rate = R.dnf_rate[drv], lap1_rate = R.lap1_rate[drv];
+        const double driver_factor = deg > 0 ? deg / 0.05 : 1.0;  // :321
+
+        // ---- _initialize_cars (:244-273) -------------------------------------------------------
+        int comp, age;
+        if (track == 2) { comp = 4; age = 0; }
+        else if (track == 1) { comp = 3; age = 0; }
+        else { comp = lane < 10 ? 0 : 1; age = lane < 10 ? 4 : 0; }
+        uint32_t used = 1u << comp;
+        bool dnf = !is_car, drs = false;
+        int dnf_lap = 0, pos_live = 0;
+        double cum = 0.0, last = 0.0, tbl = 0.0, ahead_last = 0.0;
+
+        // _calculate_lap_time :313-332, strictly left to right
+        auto lap_time = [&](int lap, double z) -> double {
+            const double effective_deg = R.cdeg[comp] * driver_factor;
+            const double tire_effect = (double)age * effective_deg;
+            const double fuel0 = 110.0 - 1.5 * (double)(lap - 1);  // every runner burns 1.5 kg per lap (exact in binary)
+            const double fuel = fuel0 > 0 ? fuel0 : 0.0;          // max(0, ...) :221 (Q11)
+            const double fuel_effect = (110.0 - fuel) * 0.03;
+            const double drs_gain = drs ? R.drs_delta : 0.0;
+            const double noise = 0.0 + sigma * z;
+            return pace + tire_effect - fuel_effect + R.cdelta[comp] - drs_gain + noise;
+        };
+        // _update_positions :538-560
+        auto update_positions = [&](int lap, bool drs_disabled) {
+            const uint32_t live_m = __ballot_sync(RFULL, !dnf);
+            const int r = rank_set(cum, live_m, lane);
+            if (!dnf) S_inv[r] = lane;
+            __syncwarp();
+            if (live_m) {
+                const int lead = (int)S_inv[0];
+                const int pl = (!dnf && r > 0) ? (int)S_inv[r - 1] : lane;
+                const double t0 = shfl_d(cum, lead), tp = shfl_d(cum, pl), lp = shfl_d(last, pl);
+                if (!dnf) {
+                    pos_live = r;
+                    tbl = cum - t0;
+                    if (lap <= 2 || drs_disabled || r == 0) drs = false;
+                    else drs = (cum - tp) < 1.0;
+                    ahead_last = r > 0 ? lp : 0.0;
+                }
+            }
+            __syncwarp();
+        };
+
+        // ---- _simulate_lap_1 (:275-311) --------------------------------------------------------
+        {
+            const double u = py.at(lane, err);
+            py.i += n;
+            if (is_car && u < lap1_rate) { dnf = true; dnf_lap = 1; }
+            const uint32_t surv = __ballot_sync(RFULL, !dnf);
+            const int k = 2 * __popc(surv & lt_mask);
+            const double z_noise = zz.at(k, err), z_start = zz.at(k + 1, err);
+            zz.i += 2 * __popc(surv);
+            if (!dnf) {
+                const double base_lap = lap_time(1, z_noise);
+                double pf = 0.5 + (double)(lane + 1) * 0.1;
+                if (pf > 1.5) pf = 1.5;
+                double sd = 0.0 + pf * z_start;
+                if (lane + 1 <= 3 && sd > 1.0) sd = 1.0;
+                const double lt = base_lap - sd * 0.5;
+                cum += lt;
+                age += 1;
+            }
+            update_positions(1, true);
+        }
+
+        int drs_until = 0;
+        for (int lap = 2; lap <= L; lap++) {
+            // ---- events :168-176 (short-circuit draws) ------------------------------------------
+            int ev = 0;
+            {
+                const double r1 = py.at(0, err); py.i++;
+                if (r1 < R.red_p) ev = 1;
+                else {
+                    const double r2 = py.at(0, err); py.i++;
+                    if (r2 < R.sc_p) ev = 2;
+                    else {
+                        const double r3 = py.at(0, err); py.i++;
+                        if (r3 < R.vsc_p) ev = 3;
+                    }
+                }
+            }
+            if (ev) {
+                const uint32_t live_m = __ballot_sync(RFULL, !dnf);
+                if (live_m) {
+                    const int lead = (int)S_inv[0];  // still the live order of the last update_positions
+                    const double t0 = shfl_d(cum, lead);
+                    const int rem = L - lap;
+                    if (ev == 1) {  // _handle_red_flag :397-431
+                        if (!dnf) {
+                            cum = t0 + (double)pos_live * 0.1;
+                            tbl = cum - t0;
+                            age = 0;
+                            comp = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
+                            used |= 1u << comp;
+                        }
+                    } else if (ev == 2) {  // _handle_safety_car :334-376 (lapped branch is dead code, Q6)
+                        if (!dnf) {
+                            cum = t0 + (double)pos_live * 0.5;
+                            tbl = cum - t0;
+                            age = age - 1 > 0 ? age - 1 : 0;
+                        }
+                    } else {  // _handle_vsc :378-395
+                        if (!dnf) {
+                            const double gap = cum - t0;
+                            cum = t0 + gap * 0.8;
+                            tbl = cum - t0;
+                        }
+                        const double r4 = py.at(0, err); py.i++;  // drawn only when somebody is still running :381-392
+                        if (r4 < 0.3 && !dnf) age = age - 1 > 0 ? age - 1 : 0;
+                    }
+                    // :179 re-sorts after the handler; a VSC can create exact ties, so re-derive the car ahead
+                    const int r = rank_set(cum, live_m, lane);
+                    __syncwarp();
+                    if (!dnf) S_inv[r] = lane;
+                    __syncwarp();
+                    const int pl = (!dnf && r > 0) ? (int)S_inv[r - 1] : lane;
+                    const double lp = shfl_d(last, pl);
+                    if (!dnf) { pos_live = r; ahead_last = r > 0 ? lp : 0.0; }
+                    __syncwarp();
+                }
+                drs_until = ev == 3 ? lap + 1 : lap + 2;
+            }
+
+            // ---- per-car lap :186-223 (grid order == lane order) -------------------------------
+            {
+                const uint32_t live_m = __ballot_sync(RFULL, !dnf);
+                const double u = py.at(__popc(live_m & lt_mask), err);
+                py.i += __popc(live_m);
+                const bool was_live = !dnf;
+                if (was_live && u < dnf_rate) { dnf = true; dnf_lap = lap; }
+                const uint32_t surv = __ballot_sync(RFULL, !dnf);
+                const double z = zz.at(__popc(surv & lt_mask), err);
+                zz.i += __popc(surv);
+                if (!dnf) {
+                    const double clean = lap_time(lap, z);
+                    double lt = clean;
+                    if (tbl > 0) {
+                        if (ahead_last > 0 && tbl < R.dirty_thr) {
+                            const double dirty = clean + R.dirty_pen;
+                            lt = dirty >= ahead_last ? dirty : ahead_last;
+                        }
+                    }
+                    cum += lt;
+                    last = lt;
+                    age += 1;
+                }
+            }
+
+            // ---- _handle_pit_stops :433-494 ----------------------------------------------------
+            {
+                const int rem = L - lap;
+                if (!dnf && (double)age > R.opt[comp][drv] && rem > 5) {
+                    cum += R.pit_loss;
+                    int nc = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
+                    const uint32_t ud = used & 7u;
+                    if (track == 0 && __popc(ud) == 1 && ((ud >> nc) & 1u)) {
+                        const uint32_t avail = 7u & ~ud;
+                        if (rem > 20) nc = (avail & 2u) ? 1 : R.pop_no_medium;
+                        else nc = (avail & 1u) ? 0 : R.pop_no_soft;
+                    }
+                    comp = nc;
+                    used |= 1u << nc;
+                    age = 0;
+                }
+            }
+
+            // ---- _simulate_overtakes :496-536 --------------------------------------------------
+            {
+                const double op = R.pace[drv] + (double)age * deg;  // :514-515 (raw driver deg)
+                for (int pass = 0; pass < 3; pass++) {
+                    const int r = rank_set(cum, nmask, lane);  // ALL cars, retired ones included (Q5)
+                    __syncwarp();
+                    if (is_car) S_inv[r] = lane;
+                    __syncwarp();
+                    const int la = (is_car && r > 0) ? (int)S_inv[r - 1] : lane;
+                    const double op_a = shfl_d(op, la);
+                    const bool dnf_a = __shfl_sync(RFULL, (int)dnf, la) != 0;
+                    double delta = op_a - op;
+                    if (drs) delta += R.drs_delta;
+                    const bool cond = is_car && r > 0 && !dnf && !dnf_a && delta > R.ovt_delta;
+                    const uint32_t CM = __reduce_or_sync(RFULL, cond ? (1u << r) : 0u);
+                    const double u = py.at(__popc(CM & ((1u << r) - 1u)), err);  // draws in sorted order :524
+                    py.i += __popc(CM);
+                    double prob = delta / 2.0;
+                    if (prob > 0.5) prob = 0.5;
+                    const bool succ = cond && u < prob;
+                    const uint32_t M = __reduce_or_sync(RFULL, succ ? (1u << r) : 0u);
+                    if (M == 0u) { __syncwarp(); break; }
+                    // sequential re-write chain :528-530, replayed op by op for bit-exactness
+                    const uint32_t clear_below = ~M & ((2u << r) - 1u);
+                    const int j = 31 - __clz(clear_below);
+                    const int k = is_car ? r - j : 0;
+                    const int lj = is_car ? (int)S_inv[j] : lane;
+                    double a = shfl_d(cum, lj);
+                    const int sn = is_car ? (int)(((M >> r) >> 1) & 1u) : 0;
+                    const int steps = k + sn;
+                    const int max_steps = __reduce_max_sync(RFULL, steps);
+                    for (int q = 0; q < max_steps; q++)
+                        if (q < steps) { a = a - 0.1; if (!(a > 0.1)) a = 0.1; }  // max(0.1, ahead - 0.1)
+                    if (steps > 0) cum = sn ? a + 0.3 : a;
+                    __syncwarp();
+                }
+            }
+            update_positions(lap, lap <= drs_until);
+        }
+
+        // ---- final classification :231-242 -------------------------------------------------------
+        {
+            const uint32_t live_m = __ballot_sync(RFULL, !dnf);
+            const int n_live = __popc(live_m & nmask);
+            int worse = 0;
+            for (int j = 0; j < n; j++) {
+                const int jl = __shfl_sync(RFULL, dnf_lap, j);
+                const double jt = shfl_d(cum, j);
+                const bool jd = __shfl_sync(RFULL, (int)dnf, j) != 0;
+                // sorted(key=(lap, cumulative_time), reverse=True) is stable: equal keys keep grid order
+                const bool ahead = jd && j != lane && (jl > dnf_lap || (jl == dnf_lap && (jt > cum || (jt == cum && j < lane))));
+                worse += ahead ? 1 : 0;
+            }
+            if (is_car) {
+                const int pos = !dnf ? pos_live : n_live + worse;
+                atomicAdd(&hist_s[drv * n + pos], 1u);
+                const unsigned long long o = s * (unsigned long long)n;
+                if (finish) finish[o + pos] = (uint8_t)drv;
+                if (times) times[o + drv] = cum;
+                if (dnf_lap_out) dnf_lap_out[o + drv] = (int16_t)dnf_lap;
+                if (grid_out) grid_out[o + lane] = (uint8_t)drv;
+            }
+            if (used_out && lane == 0) {
+                used_out[3 * s] = py.i - py0;
+                used_out[3 * s + 1] = zz.i - z0;
+                used_out[3 * s + 2] = np.i - np0;
+            }
+        }
+    }
+    if (err && status) atomicExch(status, -4);
+
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * n; i += kRThreads) {
+        const uint32_t v = hist_s[i];
+        if (v) atomicAdd(&hist[i], (unsigned long long)v);
+    }
+}
+
+cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
+                          const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
+                          double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status, int sm_count,
+                          cudaStream_t st) {
+    long long blocks = (long long)sm_count * 8;
+    const long long need = (long long)((n_sims + kRWarps - 1) / kRWarps);
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    replay_race_kernel<<<(unsigned)blocks, kRThreads, 0, st>>>(race_dev, n_sims, u_py, z, u_np, off, hist, finish, times,
+                                                            dnf_lap, grid, used, status);
+    return cudaGetLastError();
+}
+
+}  // namespace mcgp

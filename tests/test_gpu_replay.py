@@ -1,0 +1,68 @@
+"""Replay-mode CUDA path (through the C ABI) against the reference fixtures and the CPU oracle.
+
+Bar: bit-exact finishing orders, grids, DNF laps, draw consumption AND race times (north_star allows
+1e-5 relative on times; the kernel is held to 0 ulp).
+"""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _case_of(name):
+    return name.split("_h")[0] if name.rsplit("_h", 1)[-1].isdigit() else name
+
+
+@pytest.fixture(scope="module")
+def mcgp():
+    import mcgp_b200
+    return mcgp_b200
+
+
+def _replay(mcgp, oracle, cfg, mc, seed, n_sims, pop_a, pop_b):
+    oparams = oracle.make_params(cfg, mc, pop_a, pop_b)
+    ref = oracle.run_streams(oparams, oracle.Rng(seed), n_sims, detail=True, tapes=True)
+    sim = mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**cfg), pop_no_medium=pop_a, pop_no_soft=pop_b)
+    kw = {k: mc.get(k) for k in ("grid_probs", "base_pace", "tire_deg", "driver_variance", "driver_dnf_rates")}
+    got = sim.replay(**kw, track_condition=mc.get("track_condition", "dry"), u_py=ref["tape_upy"], z=ref["tape_z"],
+                     u_np=ref["tape_unp"], offsets=ref["tape_off"])
+    return ref, got
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_replay_matches_reference_fixture(mcgp, oracle, name):
+    g = load_golden(name)
+    meta = g["meta"]
+    cfg, mc, seed, _ = gc.get_case(_case_of(name))
+    n_sims = min(meta["n_sims"], 3000)
+    ref, got = _replay(mcgp, oracle, cfg, mc, seed, n_sims, meta["pop_no_medium"], meta["pop_no_soft"])
+    k = min(g["finish"].shape[0], n_sims)
+    # against the fixture recorded from the unmodified reference
+    assert np.array_equal(got["grid"][:k], g["grid"][:k]), "sampled grids differ from the reference"
+    assert np.array_equal(got["finish"][:k], g["finish"][:k]), "finishing orders differ from the reference"
+    assert np.array_equal(got["dnf_lap"][:k], g["dnf_lap"][:k])
+    assert np.array_equal(got["times"][:k].view(np.uint64), g["times"][:k].view(np.uint64)), "race times not bit-exact"
+    # against the oracle on every sim, including how many draws each sim consumed
+    assert np.array_equal(got["finish"], ref["finish"])
+    assert np.array_equal(got["times"].view(np.uint64), ref["times"].view(np.uint64))
+    assert np.array_equal(got["used"].cumsum(0), ref["draws"])
+    assert np.array_equal(got["hist"].astype(np.int64), ref["hist"])
+    if n_sims == meta["n_sims"]:
+        assert np.array_equal(got["hist"].astype(np.int64), g["hist"])
+
+
+def test_replay_tape_overrun_is_an_error(mcgp, oracle):
+    cfg, mc, seed, _ = gc.get_case("small_grids")
+    oparams = oracle.make_params(cfg, mc)
+    ref = oracle.run_streams(oparams, oracle.Rng(seed), 10, detail=True, tapes=True)
+    off = ref["tape_off"].copy()
+    off[1:, 0] -= 3  # every sim's U_py tape is 3 draws short
+    off[1:, 0] = np.maximum(off[1:, 0], off[:-1, 0])
+    sim = mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**cfg))
+    kw = {k: mc.get(k) for k in ("grid_probs", "base_pace", "tire_deg", "driver_variance", "driver_dnf_rates")}
+    with pytest.raises(mcgp.capi.McgpError) as e:
+        sim.replay(**kw, u_py=ref["tape_upy"], z=ref["tape_z"], u_np=ref["tape_unp"], offsets=off)
+    assert e.value.code == mcgp.capi.ETAPE
