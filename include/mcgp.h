@@ -93,12 +93,13 @@ int mcgp_device_info(mcgp_handle h, int* sm_count, int* sm_clock_khz, int* cc_ma
  * range is split over calls or GPUs.
  *   hist    [n_races][n][n] uint64 counts, hist[(r*n + driver)*n + pos] (pos 0 = P1), accumulated (+=)
  *           -- the reference's results[driver][position] (:93-94) before the division by n (:97-100).
- *   finish  optional, [n_races][n_sims][n] driver index per finishing position (:236-242). */
+ *   finish  optional, [n_races][n_sims][n] driver index per finishing position (:236-242).
+ *   times   optional, [n_races][n_sims][n] float: final time behind the winner, per driver index. */
 
 /* Host-buffer form: parameters are copied in, counts copied out, the call is synchronous. */
 int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims,
                     uint64_t sim_begin, uint64_t seed, uint32_t flags, uint64_t* hist_host,
-                    uint8_t* finish_host /* nullable */);
+                    uint8_t* finish_host /* nullable */, float* times_host /* nullable */);
 
 /* Device-resident form: upload the race blocks once ... */
 int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races);

@@ -58,7 +58,7 @@ _SIGNATURES = {
     "mcgp_last_launch_count": (C.c_int, [C.c_void_p]),
     "mcgp_upload_races": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int]),
     "mcgp_run_native": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int, C.c_uint64, C.c_uint64,
-                                  C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
+                                  C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcgp_launch_native": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcgp_run_replay": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_uint64] + [C.c_void_p] * 10),
@@ -134,18 +134,21 @@ class Engine:
 
     # ---- native mode ---------------------------------------------------------------------------
     def run_native(self, races, n_sims: int, sim_begin: int = 0, seed: int = 0, flags: int = 0,
-                   want_finish: bool = False, hist: np.ndarray | None = None):
-        """Host-buffer call (parameters in, counts out, synchronous).  Returns hist[n_races, n, n] uint64
-        (and finish[n_races, n_sims, n] uint8 when want_finish)."""
+                   want_finish: bool = False, hist: np.ndarray | None = None, want_times: bool = False):
+        """Host-buffer call (parameters in, counts out, synchronous).  Returns hist[n_races, n, n] uint64;
+        with want_finish also finish[n_races, n_sims, n] uint8; with want_times also times[...] float32."""
         arr, n_races, n = self._pack(races)
         if hist is None:
             hist = np.zeros((n_races, n, n), np.uint64)
         assert hist.dtype == np.uint64 and hist.shape == (n_races, n, n) and hist.flags.c_contiguous
         finish = np.zeros((n_races, n_sims, n), np.uint8) if want_finish else None
+        times = np.zeros((n_races, n_sims, n), np.float32) if want_times else None
         self._check(self._lib.mcgp_run_native(self._h, arr, n_races, n_sims, sim_begin, seed & (2 ** 64 - 1), flags,
-                                              _p(hist), _p(finish)))
+                                              _p(hist), _p(finish), _p(times)))
         self.n_races, self.n_drivers = n_races, n
-        return (hist, finish) if want_finish else hist
+        if want_finish or want_times:
+            return tuple(x for x in (hist, finish, times) if x is not None)
+        return hist
 
     def upload_races(self, races):
         arr, n_races, n = self._pack(races)

@@ -252,7 +252,7 @@ int mcgp_launch_native(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint6
 }
 
 int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims, uint64_t sim_begin,
-                    uint64_t seed, uint32_t flags, uint64_t* hist_host, uint8_t* finish_host) {
+                    uint64_t seed, uint32_t flags, uint64_t* hist_host, uint8_t* finish_host, float* times_host) {
     if (!h) return MCGP_EINVAL;
     if (!hist_host) return fail(h, MCGP_EINVAL, "hist_host is NULL");
     int rc = mcgp_upload_races(h, races, n_races);
@@ -260,14 +260,17 @@ int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, u
     const size_t n = (size_t)h->n_drivers;
     const size_t hist_bytes = (size_t)n_races * n * n * sizeof(uint64_t);
     const size_t fin_bytes = finish_host ? (size_t)n_races * n_sims * n : 0;
-    void *hist_dev = nullptr, *fin_dev = nullptr;
+    const size_t tim_bytes = times_host ? (size_t)n_races * n_sims * n * sizeof(float) : 0;
+    void *hist_dev = nullptr, *fin_dev = nullptr, *tim_dev = nullptr;
     if ((rc = scratch_get(h, 0, hist_bytes, &hist_dev))) return rc;
     if (finish_host && (rc = scratch_get(h, 1, fin_bytes, &fin_dev))) return rc;
+    if (times_host && (rc = scratch_get(h, 6, tim_bytes, &tim_dev))) return rc;
     CU(cudaMemcpy(hist_dev, hist_host, hist_bytes, cudaMemcpyHostToDevice));  // counts accumulate (+=)
-    rc = mcgp_launch_native(h, n_sims, sim_begin, seed, flags, (uint64_t*)hist_dev, (uint8_t*)fin_dev, nullptr, nullptr);
+    rc = mcgp_launch_native(h, n_sims, sim_begin, seed, flags, (uint64_t*)hist_dev, (uint8_t*)fin_dev, (float*)tim_dev, nullptr);
     if (rc) return rc;
     CU(cudaMemcpy(hist_host, hist_dev, hist_bytes, cudaMemcpyDeviceToHost));
     if (finish_host && fin_bytes) CU(cudaMemcpy(finish_host, fin_dev, fin_bytes, cudaMemcpyDeviceToHost));
+    if (times_host && tim_bytes) CU(cudaMemcpy(times_host, tim_dev, tim_bytes, cudaMemcpyDeviceToHost));
     CU(cudaDeviceSynchronize());
     return MCGP_OK;
 }

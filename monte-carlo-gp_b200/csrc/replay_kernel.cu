@@ -22,7 +22,9 @@ constexpr unsigned RFULL = 0xffffffffu;
 struct Tape {
     const double* p;
     long long i, e;
-    __device__ __forceinline__ double at(long long k, int& err) const {
+    // lanes that do not consume a draw pass active=false: they neither read nor flag an overrun
+    __device__ __forceinline__ double at(long long k, bool active, int& err) const {
+        if (!active) return 0.5;
         const long long q = i + k;
         if (q < e) return p[q];
         err = 1;
@@ -151,7 +153,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 for (int d = 1; d < n; d++) { acc = acc + S_p[d]; if (d == lane) mine = acc; }
                 __syncwarp();
                 const double cdf = mine / acc;
-                const double u = np.at(0, err); np.i++;
+                const double u = np.at(0, true, err); np.i++;
                 int sel = __popc(__ballot_sync(RFULL, is_car && cdf <= u));
                 if (sel > n - 1) sel = n - 1;
                 if (lane == pos) drv = sel;
@@ -208,12 +210,12 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
 
         // ---- _simulate_lap_1 (:275-311) --------------------------------------------------------
         {
-            const double u = py.at(lane, err);
+            const double u = py.at(lane, is_car, err);
             py.i += n;
             if (is_car && u < lap1_rate) { dnf = true; dnf_lap = 1; }
             const uint32_t surv = __ballot_sync(RFULL, !dnf);
             const int k = 2 * __popc(surv & lt_mask);
-            const double z_noise = zz.at(k, err), z_start = zz.at(k + 1, err);
+            const double z_noise = zz.at(k, !dnf, err), z_start = zz.at(k + 1, !dnf, err);
             zz.i += 2 * __popc(surv);
             if (!dnf) {
                 const double base_lap = lap_time(1, z_noise);
@@ -233,13 +235,13 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             // ---- events :168-176 (short-circuit draws) ------------------------------------------
             int ev = 0;
             {
-                const double r1 = py.at(0, err); py.i++;
+                const double r1 = py.at(0, true, err); py.i++;
                 if (r1 < R.red_p) ev = 1;
                 else {
-                    const double r2 = py.at(0, err); py.i++;
+                    const double r2 = py.at(0, true, err); py.i++;
                     if (r2 < R.sc_p) ev = 2;
                     else {
-                        const double r3 = py.at(0, err); py.i++;
+                        const double r3 = py.at(0, true, err); py.i++;
                         if (r3 < R.vsc_p) ev = 3;
                     }
                 }
@@ -270,7 +272,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                             cum = t0 + gap * 0.8;
                             tbl = cum - t0;
                         }
-                        const double r4 = py.at(0, err); py.i++;  // drawn only when somebody is still running :381-392
+                        const double r4 = py.at(0, true, err); py.i++;  // drawn only when somebody is still running :381-392
                         if (r4 < 0.3 && !dnf) age = age - 1 > 0 ? age - 1 : 0;
                     }
                     // :179 re-sorts after the handler; a VSC can create exact ties, so re-derive the car ahead
@@ -289,12 +291,12 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             // ---- per-car lap :186-223 (grid order == lane order) -------------------------------
             {
                 const uint32_t live_m = __ballot_sync(RFULL, !dnf);
-                const double u = py.at(__popc(live_m & lt_mask), err);
+                const double u = py.at(__popc(live_m & lt_mask), !dnf, err);
                 py.i += __popc(live_m);
                 const bool was_live = !dnf;
                 if (was_live && u < dnf_rate) { dnf = true; dnf_lap = lap; }
                 const uint32_t surv = __ballot_sync(RFULL, !dnf);
-                const double z = zz.at(__popc(surv & lt_mask), err);
+                const double z = zz.at(__popc(surv & lt_mask), !dnf, err);
                 zz.i += __popc(surv);
                 if (!dnf) {
                     const double clean = lap_time(lap, z);
@@ -344,7 +346,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     if (drs) delta += R.drs_delta;
                     const bool cond = is_car && r > 0 && !dnf && !dnf_a && delta > R.ovt_delta;
                     const uint32_t CM = __reduce_or_sync(RFULL, cond ? (1u << r) : 0u);
-                    const double u = py.at(__popc(CM & ((1u << r) - 1u)), err);  // draws in sorted order :524
+                    const double u = py.at(__popc(CM & ((1u << r) - 1u)), cond, err);  // draws in sorted order :524
                     py.i += __popc(CM);
                     double prob = delta / 2.0;
                     if (prob > 0.5) prob = 0.5;

@@ -1,4 +1,20 @@
-/* placeholder, filled in with the native-mode mirror */
+/* TEST INFRASTRUCTURE -- scalar CPU mirror of the native-mode (Philox / FP32) kernel; see native_mirror.c. */
 #ifndef NATIVE_MIRROR_H
 #define NATIVE_MIRROR_H
+#include "race_oracle.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Sims [sim_begin, sim_begin+n_sims) of one race with Philox key `seed` and stream id `stream`.
+ * exact != 0 selects the IEEE-only normal generator (bit-identical to the kernel's MCGP_F_EXACT_NORMAL).
+ * hist[n][n] is accumulated (+=); finish [n_sims][n] / times [n_sims][n] (float, time behind the winner,
+ * by driver index) may be NULL. */
+int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t sim_begin, int64_t n_sims, int exact,
+                   int64_t* hist, uint8_t* finish, float* times);
+
+#ifdef __cplusplus
+}
+#endif
 #endif

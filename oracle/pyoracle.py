@@ -82,6 +82,9 @@ def lib():
         L.orc_run_tapes.argtypes = [C.POINTER(OrcParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(OrcOutputs)]
         L.orc_run_tapes.restype = C.c_int
+        L.orc_run_native.argtypes = [C.POINTER(OrcParams), C.c_uint64, C.c_uint32, C.c_uint64, C.c_int64, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_run_native.restype = C.c_int
         L.orc_py_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.orc_py_sum.restype = C.c_double
         _lib = L
@@ -251,3 +254,32 @@ def run_monte_carlo(cfg: dict, mc: dict, n_sims: int, seed: int | None, pop_no_m
         hs = list(ex.map(lambda t: run_streams(params, Rng((seed or 0) + t), per[t], detail=False)["hist"],
                          range(threads)))
     return np.sum(hs, axis=0)
+
+
+def run_native(params: OrcParams, seed: int, n_sims: int, sim_begin: int = 0, stream: int = 0, exact: bool = True,
+               detail: bool = False, threads: int = 1) -> dict:
+    """Scalar mirror of the native-mode kernel (oracle/native_mirror.c)."""
+    n = params.n_drivers
+
+    def one(begin, count):
+        o = {"hist": np.zeros((n, n), np.int64)}
+        if detail:
+            o["finish"] = np.zeros((count, n), np.uint8)
+            o["times"] = np.zeros((count, n), np.float32)
+        rc = lib().orc_run_native(C.byref(params), seed & (2 ** 64 - 1), stream, begin, count, int(exact),
+                                  _ptr(o["hist"]), _ptr(o.get("finish")), _ptr(o.get("times")))
+        if rc:
+            raise RuntimeError(f"orc_run_native failed: {rc}")
+        return o
+
+    if threads <= 1 or n_sims < 4 * threads:
+        return one(sim_begin, n_sims)
+    from concurrent.futures import ThreadPoolExecutor
+    bounds = [sim_begin + n_sims * t // threads for t in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(lambda t: one(bounds[t], bounds[t + 1] - bounds[t]), range(threads)))
+    out = {"hist": np.sum([q["hist"] for q in parts], axis=0)}
+    if detail:
+        out["finish"] = np.concatenate([q["finish"] for q in parts])
+        out["times"] = np.concatenate([q["times"] for q in parts])
+    return out

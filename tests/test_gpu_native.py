@@ -1,0 +1,160 @@
+"""Native-mode CUDA path (Philox4x32-10, FP32) through the C ABI.
+
+Three gates:
+ 1. logic, exactly: with the IEEE-only normal generator the kernel must reproduce the scalar CPU mirror
+    (oracle/native_mirror.c) bit for bit -- finishing orders and final gaps of every simulated race;
+ 2. model, statistically: with the production (MUFU) normals its win / podium / position probabilities must
+    agree with the reference (FP64 oracle, itself pinned bit-exact to the unmodified reference) within 3 sigma;
+ 3. plumbing: results are independent of how a sim range is split, batches equal single launches, the
+    drop-in API returns the reference's dict shape.
+"""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from stats_util import assert_tables_agree
+
+pytestmark = pytest.mark.gpu
+
+POP = ("SOFT", "MEDIUM")
+MC_KEYS = ("grid_probs", "base_pace", "tire_deg", "driver_variance", "driver_dnf_rates")
+
+
+@pytest.fixture(scope="module")
+def mcgp():
+    import mcgp_b200
+    return mcgp_b200
+
+
+def _sim(mcgp, cfg, **kw):
+    return mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**cfg), pop_no_medium=POP[0], pop_no_soft=POP[1], **kw)
+
+
+def _params(mcgp, cfg, mc, stream=0):
+    s = _sim(mcgp, cfg)
+    return s._params(*[mc.get(k) for k in MC_KEYS], mc.get("track_condition", "dry"), stream=stream)
+
+
+@pytest.mark.parametrize("case", sorted(gc.CASES))
+def test_exact_mode_equals_cpu_mirror(mcgp, oracle, case):
+    cfg, mc, seed, _ = gc.get_case(case)
+    n_sims = 20000 if cfg["total_laps"] > 10 else 50000
+    eng = mcgp.capi.get_engine(0)
+    hist, finish, times = eng.run_native([_params(mcgp, cfg, mc, stream=3)], n_sims, sim_begin=1000, seed=seed + (7 << 32),
+                                         flags=mcgp.capi.F_EXACT_NORMAL, want_finish=True, want_times=True)
+    ref = oracle.run_native(oracle.make_params(cfg, mc, *POP), seed + (7 << 32), n_sims, sim_begin=1000, stream=3,
+                            exact=True, detail=True, threads=8)
+    bad = np.nonzero((finish[0] != ref["finish"]).any(1))[0]
+    assert bad.size == 0, f"{bad.size} of {n_sims} races differ from the CPU mirror, first: sim {bad[:5]}"
+    assert np.array_equal(times[0].view(np.uint32), ref["times"].view(np.uint32)), "final gaps not bit-identical"
+    assert np.array_equal(hist[0].astype(np.int64), ref["hist"])
+
+
+@pytest.mark.parametrize("case,n_ref,n_gpu", [("bahrain_dry", 400000, 4000000), ("monaco_sc", 250000, 4000000),
+                                               ("sprint19", 600000, 4000000), ("attrition", 300000, 3000000),
+                                               ("damp", 200000, 2000000), ("defaults", 200000, 2000000)])
+def test_native_statistics_match_reference(mcgp, oracle, case, n_ref, n_gpu):
+    cfg, mc, seed, _ = gc.get_case(case)
+    ref = oracle.run_monte_carlo(cfg, mc, n_ref, 1234, *POP, threads=8)
+    sim = _sim(mcgp, cfg)
+    got = sim.run_monte_carlo_counts(n_gpu, *[mc.get(k) for k in MC_KEYS], seed=99,
+                                     track_condition=mc.get("track_condition", "dry"))
+    assert got.sum(0).tolist() == [n_gpu] * got.shape[0] and got.sum(1).tolist() == [n_gpu] * got.shape[0]
+    print(case, assert_tables_agree(got, n_gpu, ref, n_ref, case))
+
+
+def test_fast_and_exact_normals_agree_statistically(mcgp):
+    cfg, mc, seed, _ = gc.get_case("bahrain_dry")
+    n = 3000000
+    a = _sim(mcgp, cfg).run_monte_carlo_counts(n, *[mc.get(k) for k in MC_KEYS], seed=5)
+    b = _sim(mcgp, cfg, exact_normal=True).run_monte_carlo_counts(n, *[mc.get(k) for k in MC_KEYS], seed=6)
+    print(assert_tables_agree(a, n, b, n, "fast vs exact normals"))
+
+
+def test_sim_range_split_invariance(mcgp):
+    """Counter-based RNG keyed by the global sim index: [0,N) == [0,a) + [a,b) + [b,N) (the multi-GPU sharding)."""
+    cfg, mc, seed, _ = gc.get_case("events")
+    eng = mcgp.capi.get_engine(0)
+    p = [_params(mcgp, cfg, mc)]
+    n = 100003
+    whole = eng.run_native(p, n, 0, 77)
+    parts = np.zeros_like(whole)
+    for lo, hi in ((0, 1), (1, 40000), (40000, 99999), (99999, n)):
+        eng.run_native(p, hi - lo, lo, 77, hist=parts)
+    assert np.array_equal(whole, parts)
+    assert not np.array_equal(whole, eng.run_native(p, n, 0, 78)), "seed must matter"
+
+
+def test_batch_equals_single_launches(mcgp):
+    eng = mcgp.capi.get_engine(0)
+    wl = mcgp.workloads
+    plist = []
+    for r in (0, 6, 12, 23):
+        cfg, mc = wl.workload(f"season:{r}")
+        plist.append(_params(mcgp, cfg, mc, stream=r))
+    n = 30000
+    batch = eng.run_native(plist, n, 0, 2025)
+    for i, p in enumerate(plist):
+        assert np.array_equal(batch[i], eng.run_native([p], n, 0, 2025)[0])
+    assert not np.array_equal(batch[0], batch[1])
+
+
+def test_dropin_api_shape(mcgp):
+    cfg, mc, seed, _ = gc.get_case("bahrain_dry")
+    sim = _sim(mcgp, cfg)
+    res = sim.run_monte_carlo(n_simulations=10000, grid_probs=mc["grid_probs"], base_pace=mc["base_pace"],
+                              tire_deg=mc["tire_deg"], driver_variance=mc["driver_variance"],
+                              driver_dnf_rates=mc["driver_dnf_rates"], track_condition="dry", seed=42)
+    drivers = list(mc["grid_probs"])
+    assert set(res) == set(drivers)
+    for d in drivers:
+        assert all(isinstance(k, int) and 1 <= k <= 20 and v > 0 for k, v in res[d].items())  # only non-zero cells (Q9)
+    for pos in range(1, 21):
+        assert abs(sum(res[d].get(pos, 0) for d in drivers) - 1.0) < 1e-9
+    assert abs(sum(sum(res[d].values()) for d in drivers) - 20.0) < 1e-9
+    # same consumers as src/predictor.py:307-314
+    win = {d: res.get(d, {}).get(1, 0) for d in drivers}
+    assert max(win, key=win.get) == "VER" and 0.6 < win["VER"] < 0.75
+    # reproducible with a seed, different without
+    assert res == sim.run_monte_carlo(10000, mc["grid_probs"], mc["base_pace"], mc["tire_deg"], mc["driver_variance"],
+                                      mc["driver_dnf_rates"], seed=42)
+    assert sim.run_monte_carlo(0, mc["grid_probs"], mc["base_pace"], mc["tire_deg"], mc["driver_variance"]) == {}
+    assert sim.run_monte_carlo(10, {}, {}, {}, {}) == {}
+
+
+def test_simulate_race_returns_classification(mcgp):
+    cfg, mc, seed, _ = gc.get_case("bahrain_dry")
+    sim = _sim(mcgp, cfg)
+    grid = list(mc["grid_probs"])[::-1]
+    res = sim.simulate_race(grid, mc["base_pace"], mc["tire_deg"], mc["driver_variance"], mc["driver_dnf_rates"])
+    assert sorted(d for d, _ in res) == sorted(grid) and [p for _, p in res] == list(range(1, 21))
+    assert sim.simulate_race([], {}, {}, {}) == []
+
+
+def test_seed_none_follows_global_random_stream(mcgp):
+    """backtest_model seeds `random` once (src/validation.py:172-174); seed=None must stay reproducible (Q10)."""
+    import random
+    cfg, mc, seed, _ = gc.get_case("sprint19")
+    sim = _sim(mcgp, cfg)
+    args = [mc.get(k) for k in MC_KEYS]
+    random.seed(42)
+    a1, a2 = sim.run_monte_carlo(5000, *args), sim.run_monte_carlo(5000, *args)
+    random.seed(42)
+    b1, b2 = sim.run_monte_carlo(5000, *args), sim.run_monte_carlo(5000, *args)
+    assert a1 == b1 and a2 == b2 and a1 != a2
+
+
+def test_invalid_inputs_raise(mcgp):
+    cfg, mc, seed, _ = gc.get_case("small_grids")
+    sim = _sim(mcgp, cfg)
+    args = [mc.get(k) for k in MC_KEYS]
+    bad = {d: list(v) for d, v in mc["grid_probs"].items()}
+    bad["VER"][0] = float("nan")
+    with pytest.raises(ValueError, match="NaN"):
+        sim.run_monte_carlo(10, bad, *args[1:])
+    bad["VER"][0] = -0.1
+    with pytest.raises(ValueError, match="non-negative"):
+        sim.run_monte_carlo(10, bad, *args[1:])
+    many = {f"D{i}": [1.0 / 33] * 33 for i in range(33)}
+    with pytest.raises(ValueError, match="32"):
+        sim.run_monte_carlo(10, many, {}, {}, {})
