@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import golden_cases as gc
-from stats_util import assert_tables_agree
+from stats_util import assert_agree_two_stage
 
 pytestmark = pytest.mark.gpu
 
@@ -55,20 +55,27 @@ def test_exact_mode_equals_cpu_mirror(mcgp, oracle, case):
                                                ("damp", 200000, 2000000), ("defaults", 200000, 2000000)])
 def test_native_statistics_match_reference(mcgp, oracle, case, n_ref, n_gpu):
     cfg, mc, seed, _ = gc.get_case(case)
-    ref = oracle.run_monte_carlo(cfg, mc, n_ref, 1234, *POP, threads=8)
     sim = _sim(mcgp, cfg)
-    got = sim.run_monte_carlo_counts(n_gpu, *[mc.get(k) for k in MC_KEYS], seed=99,
-                                     track_condition=mc.get("track_condition", "dry"))
-    assert got.sum(0).tolist() == [n_gpu] * got.shape[0] and got.sum(1).tolist() == [n_gpu] * got.shape[0]
-    print(case, assert_tables_agree(got, n_gpu, ref, n_ref, case))
+    args = [mc.get(k) for k in MC_KEYS]
+
+    def gpu(n, stage):
+        got = sim.run_monte_carlo_counts(n, *args, seed=99 + stage, track_condition=mc.get("track_condition", "dry"))
+        assert got.sum(0).tolist() == [n] * got.shape[0] and got.sum(1).tolist() == [n] * got.shape[0]
+        return got
+
+    def ref(n, stage):
+        return oracle.run_monte_carlo(cfg, mc, n, 1234 + 100 * stage, *POP, threads=8)
+
+    print(case, assert_agree_two_stage(gpu, ref, n_gpu, n_ref, case))
 
 
 def test_fast_and_exact_normals_agree_statistically(mcgp):
     cfg, mc, seed, _ = gc.get_case("bahrain_dry")
-    n = 3000000
-    a = _sim(mcgp, cfg).run_monte_carlo_counts(n, *[mc.get(k) for k in MC_KEYS], seed=5)
-    b = _sim(mcgp, cfg, exact_normal=True).run_monte_carlo_counts(n, *[mc.get(k) for k in MC_KEYS], seed=6)
-    print(assert_tables_agree(a, n, b, n, "fast vs exact normals"))
+    args = [mc.get(k) for k in MC_KEYS]
+    fast, exact = _sim(mcgp, cfg), _sim(mcgp, cfg, exact_normal=True)
+    print(assert_agree_two_stage(lambda n, st: fast.run_monte_carlo_counts(n, *args, seed=5 + st),
+                                 lambda n, st: exact.run_monte_carlo_counts(n, *args, seed=50 + st),
+                                 3000000, 3000000, "fast vs exact normals"))
 
 
 def test_sim_range_split_invariance(mcgp):
