@@ -30,31 +30,35 @@ constexpr unsigned FULL = 0xffffffffu;
 // VSC tyre-age rollback probability 0.3 (src/simulation.py:392) as a 32-bit threshold
 constexpr uint32_t kVscRollThr = 1288490188u;  // floor(0.3 * 2^32)
 
-__device__ __forceinline__ uint32_t time_key(float t) {
-    // order-preserving float -> uint32 map (negative times belong to retired cars)
-    uint32_t b = __float_as_uint(t);
-    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+// 1.0f iff a < b: a single FSET.BF on sm_100 (the integer-mask form costs FSETP + SEL)
+__device__ __forceinline__ float lt_one(float a, float b) {
+    float m;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+    return m;
 }
 
-// Rank of this lane's key among the n cars, ties broken by lane.  S_key: 32 words of warp scratch.
+// Rank of this lane's time among the n cars (ascending, ties broken by lane).  S_t: 32 floats of warp scratch;
+// every lane reads all keys back with broadcast LDS.128s and counts with FSET.BF + FADD (2 instr per key, one on
+// each math pipe, four independent accumulation chains).
 template <int NV4>
-__device__ __forceinline__ int rank_by_count(uint32_t key, uint32_t* S_key, int lane, int n, uint32_t nmask) {
-    S_key[lane] = key;
+__device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int n, uint32_t nmask) {
+    S_t[lane] = t;  // lanes >= n pass +inf
     __syncwarp();
-    int cnt = 0;
-    const uint4* v4 = reinterpret_cast<const uint4*>(S_key);
+    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+    const float4* v4 = reinterpret_cast<const float4*>(S_t);
 #pragma unroll
     for (int q = 0; q < NV4; q++) {
-        uint4 v = v4[q];
-        cnt += (v.x < key) ? 1 : 0;
-        cnt += (v.y < key) ? 1 : 0;
-        cnt += (v.z < key) ? 1 : 0;
-        cnt += (v.w < key) ? 1 : 0;
+        const float4 v = v4[q];
+        c0 += lt_one(v.x, t);
+        c1 += lt_one(v.y, t);
+        c2 += lt_one(v.z, t);
+        c3 += lt_one(v.w, t);
     }
+    int cnt = (int)((c0 + c1) + (c2 + c3));
     // exact ties are measure-zero events; detect them by a hole in the rank set and fix up
-    uint32_t seen = __reduce_or_sync(FULL, lane < n ? (1u << cnt) : 0u);
+    const uint32_t seen = __reduce_or_sync(FULL, lane < n ? (1u << cnt) : 0u);
     if (seen != nmask) {
-        for (int j = 0; j < lane; j++) cnt += (S_key[j] == key) ? 1 : 0;
+        for (int j = 0; j < lane; j++) cnt += (S_t[j] == t) ? 1 : 0;
     }
     __syncwarp();
     return cnt;
@@ -73,11 +77,11 @@ struct Tables {  // per-lane view of the compound tables in shared memory
 template <int NV4, bool kExact, bool kDetail>
 __global__ void __launch_bounds__(kThreads, 4)
 native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_sims, unsigned long long sim_begin,
-                   uint32_t seed_lo, uint32_t seed_hi, unsigned long long* __restrict__ hist,
+                   const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
                    uint8_t* __restrict__ finish, float* __restrict__ times) {
     __shared__ NativeRace R;
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
-    __shared__ __align__(16) uint32_t S_key_all[kWarpsPerBlock][32];
+    __shared__ __align__(16) float S_t_all[kWarpsPerBlock][32];
     __shared__ uint32_t S_inv_all[kWarpsPerBlock][32];
 
     const int race = blockIdx.y;
@@ -89,30 +93,35 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* S_key = S_key_all[warp];
+    // warp-uniform values are broadcast from lane 0 so that the compiler can PROVE them uniform: every loop bound
+    // and branch below is then convergent and the warp collectives need no divergence guards (BRA.DIV/WARPSYNC)
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
+    float* S_t = S_t_all[warp];
     uint32_t* S_inv = S_inv_all[warp];
-    const int n = R.n, L = R.total_laps, track = R.track;
+    const int n = __shfl_sync(FULL, R.n, 0), L = __shfl_sync(FULL, R.total_laps, 0), track = __shfl_sync(FULL, R.track, 0);
+    const bool grid_fixed = __shfl_sync(FULL, R.grid_fixed, 0) != 0;
     const uint32_t nmask = n >= 32 ? FULL : ((1u << n) - 1u);
     const bool is_car = lane < n;
     const float pace = R.pace[lane], deg_ovt = R.deg_ovt[lane], sigma = R.sigma[lane];
     const uint32_t dnf_thr = R.dnf_thr[lane], lap1_thr = R.lap1_thr[lane];
     const float pit_loss = R.pit_loss, ovt_delta = R.ovt_delta, drs_delta = R.drs_delta;
     const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
-    const uint32_t red_thr = R.red_thr, sc_thr = R.sc_thr, vsc_thr = R.vsc_thr, stream = R.stream;
+    const uint32_t red_thr = R.red_thr, sc_thr = R.sc_thr, vsc_thr = R.vsc_thr;
+    const uint32_t stream = __shfl_sync(FULL, R.stream, 0);
+    const float kInf = __int_as_float(0x7f800000);
     const Tables tab{&R, lane};
 
     const unsigned long long warps_per_race = (unsigned long long)gridDim.x * kWarpsPerBlock;
-    for (unsigned long long s = (unsigned long long)blockIdx.x * kWarpsPerBlock + warp; s < n_sims; s += warps_per_race) {
+    for (unsigned long long s = (unsigned long long)blockIdx.x * kWarpsPerBlock + (unsigned)warp; s < n_sims; s += warps_per_race) {
         const unsigned long long sim = sim_begin + s;
         const uint32_t sim_lo = (uint32_t)sim, sim_hi = (uint32_t)(sim >> 32);
 
         // ---- _sample_grid (src/simulation.py:102-145): sequential draw without replacement -------
         int slot = 0;
-        if (R.grid_fixed) {
+        if (grid_fixed) {
             slot = R.fixed_slot[lane];
         } else {
-            const uint4 wg = philox4x32_10(sim_lo, sim_hi, (uint32_t)lane, stream, seed_lo, seed_hi);
+            const uint4 wg = philox4x32_10(sim_lo, sim_hi, (uint32_t)lane, stream, key);
             bool remaining = is_car;
             for (int pos = 0; pos < n; pos++) {
                 float p = remaining ? R.grid[pos][lane] : 0.0f;
@@ -159,7 +168,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         bool drs = false;
         int pos_live = 0;
         {
-            const uint4 w = philox4x32_10(sim_lo, sim_hi, (1u << 8) | (uint32_t)lane, stream, seed_lo, seed_hi);
+            const uint4 w = philox4x32_10(sim_lo, sim_hi, (1u << 8) | (uint32_t)lane, stream, key);
             dnf = !is_car || (w.x < lap1_thr);
             if (is_car && dnf) dnf_lap = 1;
             float z1, z2;
@@ -180,12 +189,12 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
 
         for (int lap = 1; lap <= L; lap++) {
             if (lap >= 2) {
-                const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, seed_lo, seed_hi);
+                const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, key);
                 // ---- race-interrupting events (:168-176), decided on lane 31's words ------------
                 int ev;
                 {
                     uint4 we = w;
-                    if (n == 32) we = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 32u, stream, seed_lo, seed_hi);
+                    if (n == 32) we = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 32u, stream, key);
                     int code = (we.x < red_thr) ? 1 : (we.y < sc_thr) ? 2 : (we.z < vsc_thr) ? ((we.w < kVscRollThr) ? 4 : 3) : 0;
                     ev = __shfl_sync(FULL, code, 31);
                 }
@@ -261,7 +270,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 need_rank = true;
 #pragma unroll 1
                 for (int pass = 0; pass < 3; pass++) {
-                    rank = rank_by_count<NV4>(is_car ? time_key(t) : 0xffffffffu, S_key, lane, n, nmask);
+                    rank = rank_by_count<NV4>(is_car ? t : kInf, S_t, lane, n, nmask);
                     if (is_car) S_inv[rank] = lane;
                     __syncwarp();
                     need_rank = false;
@@ -294,7 +303,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
 
             // ---- _update_positions (:538-560), plus re-basing on the leader -----------------------
             if (need_rank) {
-                rank = rank_by_count<NV4>(is_car ? time_key(t) : 0xffffffffu, S_key, lane, n, nmask);
+                rank = rank_by_count<NV4>(is_car ? t : kInf, S_t, lane, n, nmask);
                 if (is_car) S_inv[rank] = lane;
                 __syncwarp();
             }
@@ -363,13 +372,13 @@ static cudaError_t launch_nv4(const NativeRace* races_dev, int n_races, unsigned
                               unsigned long long* hist, uint8_t* finish, float* times, int blocks_per_race,
                               cudaStream_t st) {
     dim3 grid(blocks_per_race, n_races), block(kThreads);
-    const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+    const PhiloxKeys key = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
     if (exact) {
-        if (detail) native_race_kernel<NV4, true, true><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, lo, hi, hist, finish, times);
-        else native_race_kernel<NV4, true, false><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, lo, hi, hist, finish, times);
+        if (detail) native_race_kernel<NV4, true, true><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, finish, times);
+        else native_race_kernel<NV4, true, false><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, finish, times);
     } else {
-        if (detail) native_race_kernel<NV4, false, true><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, lo, hi, hist, finish, times);
-        else native_race_kernel<NV4, false, false><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, lo, hi, hist, finish, times);
+        if (detail) native_race_kernel<NV4, false, true><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, finish, times);
+        else native_race_kernel<NV4, false, false><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, finish, times);
     }
     return cudaGetLastError();
 }

@@ -6,21 +6,34 @@ namespace mcgp {
 
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
 // key = (seed_lo, seed_hi); counter = (sim_lo, sim_hi, lap<<8 | lane, race stream).
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
-    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+// The ten round keys depend only on the seed, so the host expands them once and passes them as a kernel
+// parameter: they sit in the constant bank and feed the round's 3-input XOR (LOP3) as immediate-like operands
+// instead of costing two uniform adds per round per call.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+
+__host__ __device__ inline PhiloxKeys philox_expand_key(uint32_t seed_lo, uint32_t seed_hi) {
+    PhiloxKeys k;
+    for (int r = 0; r < 10; r++) {
+        k.k0[r] = seed_lo + 0x9E3779B9u * (uint32_t)r;
+        k.k1[r] = seed_hi + 0xBB67AE85u * (uint32_t)r;
+    }
+    return k;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& key) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        uint64_t p0 = (uint64_t)M0 * c0;
-        uint64_t p1 = (uint64_t)M1 * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint64_t p0 = (uint64_t)M0 * c0;
+        const uint64_t p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[r];
         c1 = (uint32_t)p1;
         c3 = (uint32_t)p0;
         c0 = n0;
         c2 = n2;
-        k0 += W0;
-        k1 += W1;
     }
     return make_uint4(c0, c1, c2, c3);
 }

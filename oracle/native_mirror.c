@@ -98,11 +98,6 @@ static uint32_t prob_threshold(double p) {
     return (uint32_t)floor(p * 4294967296.0);
 }
 
-static uint32_t time_key(float t) {
-    uint32_t b = as_uint(t);
-    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
-}
-
 #define N32 32
 typedef struct {
     int n, L, track;
@@ -161,9 +156,9 @@ static void order_all(const ncar* cars, int n, int* ord) {
     for (int i = 0; i < n; i++) ord[i] = i;
     for (int a = 1; a < n; a++) {
         int v = ord[a];
-        uint32_t kv = time_key(cars[v].t);
+        float tv = cars[v].t;
         int b = a - 1;
-        while (b >= 0 && (time_key(cars[ord[b]].t) > kv || (time_key(cars[ord[b]].t) == kv && ord[b] > v))) { ord[b + 1] = ord[b]; b--; }
+        while (b >= 0 && (cars[ord[b]].t > tv || (cars[ord[b]].t == tv && ord[b] > v))) { ord[b + 1] = ord[b]; b--; }
         ord[b + 1] = v;
     }
 }
