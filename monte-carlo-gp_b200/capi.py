@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libmcgp.so")
+LIB_PATH = os.environ.get("MCGP_LIB_PATH") or os.path.join(PKG_DIR, "libmcgp.so")  # override: A/B builds of the kernel
 MAX_DRIVERS, N_COMPOUNDS = 32, 5
 COMPOUNDS = ("SOFT", "MEDIUM", "HARD", "INTERMEDIATE", "WET")
 TRACK_CONDITIONS = {"dry": 0, "damp": 1, "wet": 2}

@@ -23,6 +23,9 @@
 
 namespace mcgp {
 
+#ifndef MCGP_MIN_BLOCKS
+#define MCGP_MIN_BLOCKS 4  // resident 256-thread blocks per SM the register budget is tuned for
+#endif
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned FULL = 0xffffffffu;
@@ -44,10 +47,11 @@ template <int NV4>
 __device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int n, uint32_t nmask) {
     S_t[lane] = t;  // lanes >= n pass +inf
     __syncwarp();
-    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
     const float4* v4 = reinterpret_cast<const float4*>(S_t);
+    const float4 v0 = v4[0];
+    float c0 = lt_one(v0.x, t), c1 = lt_one(v0.y, t), c2 = lt_one(v0.z, t), c3 = lt_one(v0.w, t);
 #pragma unroll
-    for (int q = 0; q < NV4; q++) {
+    for (int q = 1; q < NV4; q++) {
         const float4 v = v4[q];
         c0 += lt_one(v.x, t);
         c1 += lt_one(v.y, t);
@@ -75,7 +79,7 @@ struct Tables {  // per-lane view of the compound tables in shared memory
 };
 
 template <int NV4, bool kExact, bool kDetail>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, MCGP_MIN_BLOCKS)
 native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_sims, unsigned long long sim_begin,
                    const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
                    uint8_t* __restrict__ finish, float* __restrict__ times) {
@@ -166,7 +170,6 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         int dnf_lap = 0;
         float t, last = 0.0f, ahead_last = 0.0f;
         bool drs = false;
-        int pos_live = 0;
         {
             const uint4 w = philox4x32_10(sim_lo, sim_hi, (1u << 8) | (uint32_t)lane, stream, key);
             dnf = !is_car || (w.x < lap1_thr);
@@ -185,49 +188,54 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
 
         int drs_until = 0;
         int rank = 0;
-        bool need_rank = true;
+        bool have_rank = false;  // warp-uniform: `rank` / S_inv describe the current times
+
+        // live cars' rank among the runners, derived on demand from the all-cars rank (events, classification)
+        auto live_position = [&]() -> int {
+            const uint32_t LM = __reduce_or_sync(FULL, !dnf ? (1u << rank) : 0u);
+            return __popc(LM & ((1u << rank) - 1u));
+        };
 
         for (int lap = 1; lap <= L; lap++) {
             if (lap >= 2) {
                 const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, key);
+                const int rem = L - lap;
                 // ---- race-interrupting events (:168-176), decided on lane 31's words ------------
-                int ev;
                 {
                     uint4 we = w;
                     if (n == 32) we = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 32u, stream, key);
-                    int code = (we.x < red_thr) ? 1 : (we.y < sc_thr) ? 2 : (we.z < vsc_thr) ? ((we.w < kVscRollThr) ? 4 : 3) : 0;
-                    ev = __shfl_sync(FULL, code, 31);
-                }
-                const int rem = L - lap;
-                const int nc_rule = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
-                if (ev) {
-                    if (ev == 1) {  // _handle_red_flag :397-431
-                        if (!dnf) {
-                            t = __fmul_rn(0.1f, (float)pos_live);
-                            age = 0.0f;
-                            comp = nc_rule;
-                            used |= 1u << comp;
-                            tab.load(comp, pace, eff, opt, pc);
+                    const bool any_ev = (we.x < red_thr) || (we.y < sc_thr) || (we.z < vsc_thr);
+                    if (__shfl_sync(FULL, (int)any_ev, 31)) {  // rare (2.7 % of laps with the product probabilities)
+                        const int code = (we.x < red_thr) ? 1 : (we.y < sc_thr) ? 2 : ((we.w < kVscRollThr) ? 4 : 3);
+                        const int ev = __shfl_sync(FULL, code, 31);
+                        const int pos_live = live_position();
+                        if (ev == 1) {  // _handle_red_flag :397-431
+                            if (!dnf) {
+                                t = __fmul_rn(0.1f, (float)pos_live);
+                                age = 0.0f;
+                                comp = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
+                                used |= 1u << comp;
+                                tab.load(comp, pace, eff, opt, pc);
+                            }
+                            drs_until = lap + 2;
+                        } else if (ev == 2) {  // _handle_safety_car :334-376
+                            if (!dnf) {
+                                t = __fmul_rn(0.5f, (float)pos_live);
+                                age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
+                            }
+                            drs_until = lap + 2;
+                        } else {  // _handle_vsc :378-395
+                            if (!dnf) {
+                                t = __fmul_rn(t, 0.8f);
+                                if (ev == 4) age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
+                            }
+                            drs_until = lap + 1;
                         }
-                        drs_until = lap + 2;
-                    } else if (ev == 2) {  // _handle_safety_car :334-376
-                        if (!dnf) {
-                            t = __fmul_rn(0.5f, (float)pos_live);
-                            age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
-                        }
-                        drs_until = lap + 2;
-                    } else {  // _handle_vsc :378-395
-                        if (!dnf) {
-                            t = __fmul_rn(t, 0.8f);
-                            if (ev == 4) age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
-                        }
-                        drs_until = lap + 1;
                     }
                 }
 
                 // ---- per-car lap (:186-223) ----------------------------------------------------
-                const bool was_live = !dnf;
-                if (was_live && w.x < dnf_thr) { dnf = true; dnf_lap = lap; }
+                if (!dnf && w.x < dnf_thr) { dnf = true; dnf_lap = lap; }
                 float z, zunused;
                 if (kExact) exact_normal2(w.y, w.z, z, zunused); else z = fast_normal(w.y, w.z);
                 // _calculate_lap_time :313-332 (fuel is lap-uniform: every runner burns 1.5 kg per lap)
@@ -246,11 +254,11 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 }
 
                 // ---- _handle_pit_stops (:433-494) ----------------------------------------------
-                const bool pit = !dnf && rem > 5 && age > opt;
+                const bool pit = !dnf && age > opt && rem > 5;
                 if (__any_sync(FULL, pit)) {
                     if (pit) {
                         t = __fadd_rn(t, pit_loss);
-                        int nc = nc_rule;
+                        int nc = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
                         const uint32_t ud = used & 7u;
                         if (track == 0 && __popc(ud) == 1 && ((ud >> nc) & 1u)) {  // two-compound rule :481-488
                             const uint32_t avail = 7u & ~ud;
@@ -266,46 +274,60 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
 
                 // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
                 const float op = dnf ? __int_as_float(0x7fc00000) : __fmaf_rn(age, deg_ovt, pace);  // NaN blocks the pair (Q5)
-                const uint32_t u3 = ((w.y & 0xffu) << 8) | (w.z & 0xffu);
-                need_rank = true;
+                have_rank = false;
 #pragma unroll 1
                 for (int pass = 0; pass < 3; pass++) {
-                    rank = rank_by_count<NV4>(is_car ? t : kInf, S_t, lane, n, nmask);
-                    if (is_car) S_inv[rank] = lane;
-                    __syncwarp();
-                    need_rank = false;
+                    if (!have_rank) {
+                        rank = rank_by_count<NV4>(is_car ? t : kInf, S_t, lane, n, nmask);
+                        if (is_car) S_inv[rank] = lane;
+                        __syncwarp();
+                        have_rank = true;
+                    }
                     const int la = (is_car && rank > 0) ? (int)S_inv[rank - 1] : lane;
                     const float op_a = __shfl_sync(FULL, op, la);
                     float delta = __fadd_rn(op_a, -op);
                     if (drs) delta = __fadd_rn(delta, drs_delta);
-                    const uint32_t u16 = pass == 0 ? (w.w & 0xffffu) : pass == 1 ? (w.w >> 16) : u3;
-                    const float u = __fmul_rn((float)u16, 1.52587890625e-05f);
-                    const float prob = fminf(0.5f, __fmul_rn(delta, 0.5f));
-                    const bool succ = is_car && rank > 0 && delta > ovt_delta && u < prob;
+                    const uint32_t u16 = pass == 0 ? (w.w & 0xffffu) : pass == 1 ? (w.w >> 16) : (((w.y & 0xffu) << 8) | (w.z & 0xffu));
+                    // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling)
+                    const float thr = fminf(32768.0f, __fmul_rn(delta, 32768.0f));
+                    const bool succ = is_car && rank > 0 && delta > ovt_delta && (float)u16 < thr;
                     const uint32_t M = __reduce_or_sync(FULL, succ ? (1u << rank) : 0u);
                     if (M == 0u) break;
-                    // closed form of the sequential re-write chain :522-531 over runs of successes
+                    // closed form of the sequential re-write chain :522-531 over runs of consecutive successes
                     const uint32_t clear_below = ~M & ((2u << rank) - 1u);
                     const int j = 31 - __clz(clear_below);  // run start (bit 0 of M is never set)
                     const int k = rank - j;
                     const int lj = is_car ? (int)S_inv[j] : lane;
                     const float base = __shfl_sync(FULL, t, lj);
-                    const int sn = (int)(((M >> rank) >> 1) & 1u);
+                    const uint32_t above = ~((M >> rank) >> 1);  // bit i clear <=> pair (rank+i, rank+i+1) swapped
+                    const int sn = (int)(~above & 1u);
                     if (is_car && (k + sn) > 0) {
                         float v = __fmaf_rn(-0.1f, (float)(k + sn), base);
                         if (sn) v = __fadd_rn(v, 0.3f);
                         t = v;
                     }
+                    // The new order is almost always the old one with every run [j, e] reversed (the re-written times
+                    // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
+                    // Verify the presumed order with one neighbour compare instead of re-counting all 20 ranks.
+                    const int e = rank + (__ffs(above) - 1);  // run end
+                    const int r2 = j + e - rank;
                     __syncwarp();
-                    need_rank = true;
+                    if (is_car) { S_t[r2] = t; S_inv[r2] = lane; }
+                    __syncwarp();
+                    const float prev = S_t[(is_car && r2 > 0) ? r2 - 1 : 0];
+                    const bool bad = is_car && r2 > 0 && !(prev < t);
+                    have_rank = !__any_sync(FULL, bad);
+                    if (have_rank) rank = r2;
+                    __syncwarp();
                 }
             }
 
             // ---- _update_positions (:538-560), plus re-basing on the leader -----------------------
-            if (need_rank) {
+            if (!have_rank) {
                 rank = rank_by_count<NV4>(is_car ? t : kInf, S_t, lane, n, nmask);
                 if (is_car) S_inv[rank] = lane;
                 __syncwarp();
+                have_rank = true;
             }
             {
                 const bool live = !dnf;
@@ -318,7 +340,6 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                     const int pl = has_pred ? (int)S_inv[31 - __clz(below)] : lane;
                     const float t_pred = __shfl_sync(FULL, t, pl);
                     const float last_pred = __shfl_sync(FULL, last, pl);
-                    pos_live = __popc(below);
                     const bool drs_on = lap > 2 && lap > drs_until;
                     if (live) {
                         drs = has_pred && drs_on && (__fadd_rn(t, -t_pred) < 1.0f);
@@ -329,6 +350,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 __syncwarp();
             }
         }
+        const int pos_live = live_position();
 
         // ---- final classification (:231-242) -----------------------------------------------------
         {
@@ -388,7 +410,7 @@ cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, u
                           unsigned long long* hist, uint8_t* finish, float* times, int sm_count, cudaStream_t st) {
     const bool detail = finish != nullptr || times != nullptr;
     // persistent-style grid: 4 resident blocks per SM, split evenly over the races of the batch
-    const long long resident = (long long)sm_count * 4;
+    const long long resident = (long long)sm_count * MCGP_MIN_BLOCKS;
     long long bpr = (resident + n_races - 1) / n_races;
     const long long need = (long long)((n_sims + kWarpsPerBlock - 1) / kWarpsPerBlock);
     if (bpr > need) bpr = need;

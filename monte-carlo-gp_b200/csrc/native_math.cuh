@@ -41,7 +41,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // ---- fast normals: Box-Muller on the MUFU unit (lg2 / sqrt / sin / cos approximations) --------
 __device__ __forceinline__ float fast_radius(uint32_t w) {
     // u = ((w>>8)+1) * 2^-24 in (0,1];  r = sqrt(-2 ln u) = sqrt(-2 ln2 * (lg2(k) - 24))
-    float lg = __log2f((float)((w >> 8) + 1u));
+    float lg;  // the argument is an integer in [1, 2^24]: no denormal guard needed around MUFU.LG2
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)((w >> 8) + 1u)));
     float r2 = fmaxf(__fmaf_rn(lg, -1.3862943611198906f, 33.27106466687737f), 0.0f);
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
