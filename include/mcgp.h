@@ -108,6 +108,23 @@ int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races)
  * times_dev: optional [n_races][n_sims][n] float, final time behind the winner per driver index. */
 int mcgp_launch_native(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
                        uint64_t* hist_dev, uint8_t* finish_dev, float* times_dev, void* cuda_stream);
+/* Optional per-lap trace (BASELINE config 5; an output the reference does not have): one 8-byte record per
+ * (sim, lap, driver) for the sims [trace_first, trace_first + trace_count) of the launched range (indices relative
+ * to sim_begin), laid out trace[race][sim - trace_first][lap - 1][driver].  9.1 KB per 20-driver x 57-lap race. */
+typedef struct mcgp_trace_record {
+    uint8_t position; /* running position after the lap (1 = leader), 0 = retired                               */
+    uint8_t compound; /* MCGP_SOFT .. MCGP_WET                                                                    */
+    uint8_t tire_age; /* laps on the current set                                                                  */
+    uint8_t flags;    /* bit0 retired, bit1 DRS armed for the next lap, bit2 pitted this lap, bits4-5 event this lap
+                         (1 red flag, 2 safety car, 3 VSC)                                                         */
+    float gap;        /* seconds behind the leader                                                                 */
+} mcgp_trace_record;
+int mcgp_launch_native_traced(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
+                              uint64_t* hist_dev, mcgp_trace_record* trace_dev, uint64_t trace_first,
+                              uint64_t trace_count, void* cuda_stream);
+int mcgp_run_native_traced(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims,
+                           uint64_t sim_begin, uint64_t seed, uint32_t flags, uint64_t* hist_host,
+                           mcgp_trace_record* trace_host, uint64_t trace_first, uint64_t trace_count);
 /* Number of kernel launches the last mcgp_launch_native / mcgp_run_* call on this handle made. */
 int mcgp_last_launch_count(mcgp_handle h);
 

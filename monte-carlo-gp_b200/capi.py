@@ -40,6 +40,11 @@ class McgpRaceParams(C.Structure):
     ]
 
 
+# mcgp_trace_record (include/mcgp.h): one record per (sim, lap, driver)
+TRACE_DTYPE = np.dtype([("position", np.uint8), ("compound", np.uint8), ("tire_age", np.uint8), ("flags", np.uint8),
+                        ("gap", np.float32)])
+
+
 class McgpError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmcgp error {code}: {msg}")
@@ -61,6 +66,10 @@ _SIGNATURES = {
                                   C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcgp_launch_native": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcgp_launch_native_traced": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p,
+                                            C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "mcgp_run_native_traced": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int, C.c_uint64, C.c_uint64,
+                                         C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "mcgp_run_replay": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_uint64] + [C.c_void_p] * 10),
     "mcgp_launch_replay": (C.c_int, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 12),
 }
@@ -149,6 +158,25 @@ class Engine:
         if want_finish or want_times:
             return tuple(x for x in (hist, finish, times) if x is not None)
         return hist
+
+    def run_native_traced(self, races, n_sims: int, sim_begin: int = 0, seed: int = 0, flags: int = 0,
+                          trace_first: int = 0, trace_count: int | None = None):
+        """Host-buffer call with the per-lap trace of sims [trace_first, trace_first+trace_count) of the range.
+        Returns (hist, trace) with trace a structured array [n_races, trace_count, laps, n] of TRACE_DTYPE."""
+        arr, n_races, n = self._pack(races)
+        trace_count = n_sims - trace_first if trace_count is None else trace_count
+        laps = races[0].total_laps
+        hist = np.zeros((n_races, n, n), np.uint64)
+        trace = np.zeros((n_races, trace_count, laps, n), TRACE_DTYPE)
+        self._check(self._lib.mcgp_run_native_traced(self._h, arr, n_races, n_sims, sim_begin, seed & (2 ** 64 - 1), flags,
+                                                     _p(hist), _p(trace), trace_first, trace_count))
+        self.n_races, self.n_drivers = n_races, n
+        return hist, trace
+
+    def launch_native_traced(self, n_sims, sim_begin, seed, hist_ptr, trace_ptr, trace_first, trace_count, flags=0,
+                             stream=None):
+        self._check(self._lib.mcgp_launch_native_traced(self._h, n_sims, sim_begin, seed & (2 ** 64 - 1), flags, _p(hist_ptr),
+                                                        _p(trace_ptr), trace_first, trace_count, _p(stream)))
 
     def upload_races(self, races):
         arr, n_races, n = self._pack(races)

@@ -41,3 +41,13 @@ struct ReplayRace {
     double grid[MCGP_LANES][MCGP_LANES];     // [driver][pos]
     uint8_t kind[MCGP_LANES][MCGP_LANES];    // MCGP_ITEM_*
 };
+
+// ---- optional per-lap trace (BASELINE config 5; absent upstream) -------------------------------
+// One record per (sim, lap, driver).  Same layout as mcgp_trace_record in include/mcgp.h.
+struct TraceRecord {
+    uint8_t position;  // 1-based running position after the lap, 0 = retired
+    uint8_t compound;  // MCGP_SOFT .. MCGP_WET
+    uint8_t tire_age;  // laps on the current set
+    uint8_t flags;     // bit0 retired, bit1 DRS enabled for the next lap, bit2 pitted this lap, bits4-5 event (1 red, 2 SC, 3 VSC)
+    float gap;         // seconds behind the leader (retired cars: frozen time relative to the leader)
+};

@@ -14,7 +14,8 @@
 namespace mcgp {
 cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, unsigned long long n_sims,
                           unsigned long long sim_begin, unsigned long long seed, bool exact,
-                          unsigned long long* hist, uint8_t* finish, float* times, int sm_count, cudaStream_t st);
+                          unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
+                          unsigned long long trace_first, unsigned long long trace_count, int sm_count, cudaStream_t st);
 cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status, int sm_count,
@@ -237,17 +238,59 @@ int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races)
     return MCGP_OK;
 }
 
-int mcgp_launch_native(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
-                       uint64_t* hist_dev, uint8_t* finish_dev, float* times_dev, void* cuda_stream) {
+static int launch_native_common(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
+                                uint64_t* hist_dev, uint8_t* finish_dev, float* times_dev, mcgp_trace_record* trace_dev,
+                                uint64_t trace_first, uint64_t trace_count, void* cuda_stream) {
     if (!h) return MCGP_EINVAL;
     if (!h->native_dev) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
     if (!hist_dev) return fail(h, MCGP_EINVAL, "hist_dev is NULL");
     h->launches = 0;
     if (n_sims == 0) return MCGP_OK;
+    if (trace_dev && (trace_first > n_sims || trace_count > n_sims - trace_first))
+        return fail(h, MCGP_EINVAL, "trace window exceeds the launched sim range");
     CU(cudaSetDevice(h->device));
+    static_assert(sizeof(mcgp_trace_record) == sizeof(TraceRecord) && sizeof(TraceRecord) == 8, "trace record layout");
     CU(mcgp::launch_native(h->native_dev, h->n_races, h->n_drivers, n_sims, sim_begin, seed, (flags & MCGP_F_EXACT_NORMAL) != 0,
-                           (unsigned long long*)hist_dev, finish_dev, times_dev, h->sm_count, (cudaStream_t)cuda_stream));
+                           (unsigned long long*)hist_dev, finish_dev, times_dev, (TraceRecord*)(trace_count ? trace_dev : nullptr),
+                           trace_first, trace_count, h->sm_count, (cudaStream_t)cuda_stream));
     h->launches = 1;
+    return MCGP_OK;
+}
+
+int mcgp_launch_native(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
+                       uint64_t* hist_dev, uint8_t* finish_dev, float* times_dev, void* cuda_stream) {
+    return launch_native_common(h, n_sims, sim_begin, seed, flags, hist_dev, finish_dev, times_dev, nullptr, 0, 0, cuda_stream);
+}
+
+int mcgp_launch_native_traced(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
+                              uint64_t* hist_dev, mcgp_trace_record* trace_dev, uint64_t trace_first, uint64_t trace_count,
+                              void* cuda_stream) {
+    if (h && !trace_dev) return fail(h, MCGP_EINVAL, "trace_dev is NULL");
+    return launch_native_common(h, n_sims, sim_begin, seed, flags, hist_dev, nullptr, nullptr, trace_dev, trace_first, trace_count, cuda_stream);
+}
+
+int mcgp_run_native_traced(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims, uint64_t sim_begin,
+                           uint64_t seed, uint32_t flags, uint64_t* hist_host, mcgp_trace_record* trace_host,
+                           uint64_t trace_first, uint64_t trace_count) {
+    if (!h) return MCGP_EINVAL;
+    if (!hist_host || !trace_host) return fail(h, MCGP_EINVAL, "NULL output pointer");
+    int rc = mcgp_upload_races(h, races, n_races);
+    if (rc) return rc;
+    const size_t n = (size_t)h->n_drivers;
+    const size_t hist_bytes = (size_t)n_races * n * n * sizeof(uint64_t);
+    const size_t tr_bytes = (size_t)n_races * trace_count * (size_t)races[0].total_laps * n * sizeof(mcgp_trace_record);
+    for (int r = 1; r < n_races; r++)
+        if (races[r].total_laps != races[0].total_laps) return fail(h, MCGP_EINVAL, "traced batches need equal total_laps");
+    void *hist_dev = nullptr, *tr_dev = nullptr;
+    if ((rc = scratch_get(h, 0, hist_bytes, &hist_dev))) return rc;
+    if ((rc = scratch_get(h, 6, tr_bytes, &tr_dev))) return rc;
+    CU(cudaMemcpy(hist_dev, hist_host, hist_bytes, cudaMemcpyHostToDevice));
+    rc = mcgp_launch_native_traced(h, n_sims, sim_begin, seed, flags, (uint64_t*)hist_dev, (mcgp_trace_record*)tr_dev, trace_first,
+                                   trace_count, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpy(hist_host, hist_dev, hist_bytes, cudaMemcpyDeviceToHost));
+    if (tr_bytes) CU(cudaMemcpy(trace_host, tr_dev, tr_bytes, cudaMemcpyDeviceToHost));
+    CU(cudaDeviceSynchronize());
     return MCGP_OK;
 }
 

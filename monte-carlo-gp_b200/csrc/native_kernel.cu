@@ -78,11 +78,23 @@ struct Tables {  // per-lane view of the compound tables in shared memory
     }
 };
 
-template <int NV4, bool kExact, bool kDetail>
+// per-sim outputs beyond the count table (all optional)
+struct NativeOutputs {
+    uint8_t* finish;            // [race][sim][pos]  driver index
+    float* times;               // [race][sim][driver] final gap to the winner
+    TraceRecord* trace;         // [race][sim - trace_first][lap][driver]
+    unsigned long long trace_first, trace_count;  // window of sims (indices within the launch) that are traced
+};
+
+// kOut: 0 = count table only, 1 = + finish/times, 2 = + per-lap trace
+template <int NV4, bool kExact, int kOut>
 __global__ void __launch_bounds__(kThreads, MCGP_MIN_BLOCKS)
 native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_sims, unsigned long long sim_begin,
                    const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
-                   uint8_t* __restrict__ finish, float* __restrict__ times) {
+                   const __grid_constant__ NativeOutputs out) {
+    constexpr bool kDetail = kOut >= 1, kTrace = kOut >= 2;
+    uint8_t* __restrict__ finish = out.finish;
+    float* __restrict__ times = out.times;
     __shared__ NativeRace R;
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     __shared__ __align__(16) float S_t_all[kWarpsPerBlock][32];
@@ -189,6 +201,9 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         int drs_until = 0;
         int rank = 0;
         bool have_rank = false;  // warp-uniform: `rank` / S_inv describe the current times
+        const bool traced = kTrace && s >= out.trace_first && s - out.trace_first < out.trace_count;
+        int tr_event = 0;
+        bool tr_pit = false;
 
         // live cars' rank among the runners, derived on demand from the all-cars rank (events, classification)
         auto live_position = [&]() -> int {
@@ -209,6 +224,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                         const int code = (we.x < red_thr) ? 1 : (we.y < sc_thr) ? 2 : ((we.w < kVscRollThr) ? 4 : 3);
                         const int ev = __shfl_sync(FULL, code, 31);
                         const int pos_live = live_position();
+                        if (kTrace) tr_event = ev > 3 ? 3 : ev;
                         if (ev == 1) {  // _handle_red_flag :397-431
                             if (!dnf) {
                                 t = __fmul_rn(0.1f, (float)pos_live);
@@ -255,6 +271,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
 
                 // ---- _handle_pit_stops (:433-494) ----------------------------------------------
                 const bool pit = !dnf && age > opt && rem > 5;
+                if (kTrace) tr_pit = pit;
                 if (__any_sync(FULL, pit)) {
                     if (pit) {
                         t = __fadd_rn(t, pit_loss);
@@ -349,6 +366,22 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 }
                 __syncwarp();
             }
+            if (kTrace) {
+                if (traced) {  // one 8-byte record per driver per lap: 160 contiguous bytes per warp
+                    const int pl = live_position();
+                    if (is_car) {
+                        TraceRecord rec;
+                        rec.position = dnf ? 0 : (uint8_t)(pl + 1);
+                        rec.compound = (uint8_t)comp;
+                        rec.tire_age = (uint8_t)(int)age;
+                        rec.flags = (uint8_t)((dnf ? 1 : 0) | (drs ? 2 : 0) | (tr_pit ? 4 : 0) | (tr_event << 4));
+                        rec.gap = t;
+                        out.trace[(((unsigned long long)race * out.trace_count + (s - out.trace_first)) * (unsigned)L + (unsigned)(lap - 1)) * (unsigned)n + lane] = rec;
+                    }
+                }
+                tr_event = 0;
+                tr_pit = false;
+            }
         }
         const int pos_live = live_position();
 
@@ -388,36 +421,36 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
 }
 
 // ---- host-side launcher ------------------------------------------------------------------------
-template <int NV4>
-static cudaError_t launch_nv4(const NativeRace* races_dev, int n_races, unsigned long long n_sims,
-                              unsigned long long sim_begin, unsigned long long seed, bool exact, bool detail,
-                              unsigned long long* hist, uint8_t* finish, float* times, int blocks_per_race,
-                              cudaStream_t st) {
-    dim3 grid(blocks_per_race, n_races), block(kThreads);
-    const PhiloxKeys key = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
-    if (exact) {
-        if (detail) native_race_kernel<NV4, true, true><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, finish, times);
-        else native_race_kernel<NV4, true, false><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, finish, times);
-    } else {
-        if (detail) native_race_kernel<NV4, false, true><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, finish, times);
-        else native_race_kernel<NV4, false, false><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, finish, times);
-    }
-    return cudaGetLastError();
+template <int NV4, bool kExact>
+static void launch_out(int kout, dim3 grid, dim3 block, cudaStream_t st, const NativeRace* races_dev, unsigned long long n_sims,
+                       unsigned long long sim_begin, const PhiloxKeys& key, unsigned long long* hist, const NativeOutputs& out) {
+    if (kout == 0) native_race_kernel<NV4, kExact, 0><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out);
+    else if (kout == 1) native_race_kernel<NV4, kExact, 1><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out);
+    else native_race_kernel<NV4, kExact, 2><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out);
 }
 
 cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, unsigned long long n_sims,
                           unsigned long long sim_begin, unsigned long long seed, bool exact,
-                          unsigned long long* hist, uint8_t* finish, float* times, int sm_count, cudaStream_t st) {
-    const bool detail = finish != nullptr || times != nullptr;
-    // persistent-style grid: 4 resident blocks per SM, split evenly over the races of the batch
+                          unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
+                          unsigned long long trace_first, unsigned long long trace_count, int sm_count, cudaStream_t st) {
+    const int kout = trace ? 2 : (finish != nullptr || times != nullptr) ? 1 : 0;
+    // persistent-style grid: MCGP_MIN_BLOCKS resident blocks per SM, split evenly over the races of the batch
     const long long resident = (long long)sm_count * MCGP_MIN_BLOCKS;
     long long bpr = (resident + n_races - 1) / n_races;
     const long long need = (long long)((n_sims + kWarpsPerBlock - 1) / kWarpsPerBlock);
     if (bpr > need) bpr = need;
     if (bpr < 1) bpr = 1;
-    if (max_n <= 20)
-        return launch_nv4<5>(races_dev, n_races, n_sims, sim_begin, seed, exact, detail, hist, finish, times, (int)bpr, st);
-    return launch_nv4<8>(races_dev, n_races, n_sims, sim_begin, seed, exact, detail, hist, finish, times, (int)bpr, st);
+    const dim3 grid((unsigned)bpr, n_races), block(kThreads);
+    const PhiloxKeys key = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    const NativeOutputs out{finish, times, trace, trace_first, trace ? trace_count : 0ull};
+    if (max_n <= 20) {
+        if (exact) launch_out<5, true>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out);
+        else launch_out<5, false>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out);
+    } else {
+        if (exact) launch_out<8, true>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out);
+        else launch_out<8, false>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out);
+    }
+    return cudaGetLastError();
 }
 
 }  // namespace mcgp

@@ -183,8 +183,24 @@ static void update_positions(ncar* cars, int n, int lap, int drs_until) {
     if (have) for (int d = 0; d < n; d++) cars[d].t = cars[d].t + -tl;
 }
 
+typedef struct { uint8_t position, compound, tire_age, flags; float gap; } trace_rec;
+
+static void emit_trace(trace_rec* trace, int64_t s, int L, int n, int lap, const ncar* cars, const int* pitted, int ev) {
+    if (!trace) return;
+    for (int d = 0; d < n; d++) {
+        trace_rec* r = &trace[((s * L) + (lap - 1)) * n + d];
+        r->position = cars[d].dnf ? 0 : (uint8_t)(cars[d].pos_live + 1);
+        r->compound = (uint8_t)cars[d].comp;
+        r->tire_age = (uint8_t)(int)cars[d].age;
+        r->flags = (uint8_t)((cars[d].dnf ? 1 : 0) | (cars[d].drs ? 2 : 0) | (pitted[d] ? 4 : 0) | ((ev > 3 ? 3 : ev) << 4));
+        r->gap = cars[d].t;
+    }
+}
+
 int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t sim_begin, int64_t n_sims, int exact,
-                   int64_t* hist, uint8_t* finish, float* times) {
+                   int64_t* hist, uint8_t* finish, float* times, void* trace_out) {
+    trace_rec* trace = (trace_rec*)trace_out;
+    int pitted[N32];
     if (p->n_drivers < 1 || p->n_drivers > N32) return -1;
     nat_t R;
     derive(p, &R);
@@ -251,6 +267,8 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
         }
         int drs_until = 0;
         update_positions(cars, n, 1, drs_until);
+        memset(pitted, 0, sizeof(pitted));
+        emit_trace(trace, s, L, n, 1, cars, pitted, 0);
 
         for (int lap = 2; lap <= L; lap++) {
             /* ---- events :168-176 ---- */
@@ -294,9 +312,11 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
                 c->age = c->age + 1.0f;
             }
             /* ---- _handle_pit_stops :433-494 ---- */
+            memset(pitted, 0, sizeof(pitted));
             for (int d = 0; d < n; d++) {
                 ncar* c = &cars[d];
                 if (c->dnf || !(rem > 5) || !(c->age > c->opt)) continue;
+                pitted[d] = 1;
                 c->t = c->t + R.pit_loss;
                 int nc = nc_rule;
                 const uint32_t ud = c->used & 7u;
@@ -341,6 +361,7 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
                 }
             }
             update_positions(cars, n, lap, drs_until);
+            emit_trace(trace, s, L, n, lap, cars, pitted, ev);
         }
         /* ---- final classification :231-242 ---- */
         int n_live = 0;

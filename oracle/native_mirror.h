@@ -12,7 +12,7 @@ extern "C" {
  * hist[n][n] is accumulated (+=); finish [n_sims][n] / times [n_sims][n] (float, time behind the winner,
  * by driver index) may be NULL. */
 int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t sim_begin, int64_t n_sims, int exact,
-                   int64_t* hist, uint8_t* finish, float* times);
+                   int64_t* hist, uint8_t* finish, float* times, void* trace /* [n_sims][laps][n] 8-byte records, or NULL */);
 
 #ifdef __cplusplus
 }

@@ -83,7 +83,7 @@ def lib():
                                     C.c_void_p, C.POINTER(OrcOutputs)]
         L.orc_run_tapes.restype = C.c_int
         L.orc_run_native.argtypes = [C.POINTER(OrcParams), C.c_uint64, C.c_uint32, C.c_uint64, C.c_int64, C.c_int,
-                                     C.c_void_p, C.c_void_p, C.c_void_p]
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_run_native.restype = C.c_int
         L.orc_py_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.orc_py_sum.restype = C.c_double
@@ -256,18 +256,26 @@ def run_monte_carlo(cfg: dict, mc: dict, n_sims: int, seed: int | None, pop_no_m
     return np.sum(hs, axis=0)
 
 
+TRACE_DTYPE = np.dtype([("position", np.uint8), ("compound", np.uint8), ("tire_age", np.uint8), ("flags", np.uint8),
+                        ("gap", np.float32)])
+
+
 def run_native(params: OrcParams, seed: int, n_sims: int, sim_begin: int = 0, stream: int = 0, exact: bool = True,
-               detail: bool = False, threads: int = 1) -> dict:
+               detail: bool = False, threads: int = 1, trace: bool = False) -> dict:
     """Scalar mirror of the native-mode kernel (oracle/native_mirror.c)."""
     n = params.n_drivers
+    if trace:
+        threads = 1
 
     def one(begin, count):
         o = {"hist": np.zeros((n, n), np.int64)}
         if detail:
             o["finish"] = np.zeros((count, n), np.uint8)
             o["times"] = np.zeros((count, n), np.float32)
+        if trace:
+            o["trace"] = np.zeros((count, params.total_laps, n), TRACE_DTYPE)
         rc = lib().orc_run_native(C.byref(params), seed & (2 ** 64 - 1), stream, begin, count, int(exact),
-                                  _ptr(o["hist"]), _ptr(o.get("finish")), _ptr(o.get("times")))
+                                  _ptr(o["hist"]), _ptr(o.get("finish")), _ptr(o.get("times")), _ptr(o.get("trace")))
         if rc:
             raise RuntimeError(f"orc_run_native failed: {rc}")
         return o

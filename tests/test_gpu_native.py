@@ -165,3 +165,25 @@ def test_invalid_inputs_raise(mcgp):
     many = {f"D{i}": [1.0 / 33] * 33 for i in range(33)}
     with pytest.raises(ValueError, match="32"):
         sim.run_monte_carlo(10, many, {}, {}, {})
+
+
+@pytest.mark.parametrize("case", ["bahrain_dry", "events", "attrition", "sprint19", "damp"])
+def test_trace_equals_cpu_mirror(mcgp, oracle, case):
+    """BASELINE config 5's optional per-lap trace: every record (position, compound, tyre age, flags, gap) of a sim
+    window equals the scalar mirror's, and tracing does not change the count table."""
+    cfg, mc, seed, _ = gc.get_case(case)
+    eng = mcgp.capi.get_engine(0)
+    p = _params(mcgp, cfg, mc)
+    n_sims, first, count = 3000, 1200, 700
+    hist, trace = eng.run_native_traced([p], n_sims, sim_begin=50, seed=seed, flags=mcgp.capi.F_EXACT_NORMAL,
+                                        trace_first=first, trace_count=count)
+    ref = oracle.run_native(oracle.make_params(cfg, mc, *POP), seed, count, sim_begin=50 + first, exact=True, trace=True)
+    assert trace.shape == (1, count, cfg["total_laps"], p.n_drivers)
+    for f in ("position", "compound", "tire_age", "flags"):
+        assert np.array_equal(trace[0][f], ref["trace"][f]), f
+    assert np.array_equal(trace[0]["gap"].view(np.uint32), ref["trace"]["gap"].view(np.uint32))
+    assert np.array_equal(hist, eng.run_native([p], n_sims, 50, seed, flags=mcgp.capi.F_EXACT_NORMAL))
+    # sanity of the records themselves: each lap's running positions are a permutation of 1..n_live
+    pos = trace[0]["position"]
+    live = pos > 0
+    assert (np.sort(np.where(live, pos, 255), axis=2)[..., 0] == np.where(live.any(2), 1, 255)).all()
