@@ -4,6 +4,7 @@
 
 #define MCGP_LANES 32
 #define MCGP_NC 5
+#define MCGP_DNF_NEVER (-1e30f)
 
 // ---- native mode (FP32 / integer thresholds) -------------------------------------------------
 // Everything a warp needs for one race.  ~6.6 KB, staged once per block into shared memory; the
@@ -21,11 +22,12 @@ struct NativeRace {
     float pace[MCGP_LANES];                  // base_pace
     float deg_ovt[MCGP_LANES];               // raw tire_deg (overtake pace, src/simulation.py:514)
     float sigma[MCGP_LANES];                 // driver_variance
-    uint32_t dnf_thr[MCGP_LANES];            // per-lap DNF threshold, laps >= 2
+    float dnf_scale[MCGP_LANES];             // 1 / ln(1 - dnf_rate) <= 0: retirement lap = 2 + floor(ln(u) * dnf_scale);
+                                             // MCGP_DNF_NEVER for rate <= 0 (laps >= 2, src/simulation.py:190-197)
     uint32_t lap1_thr[MCGP_LANES];           // 4 x team rate, lap 1
     float eff_deg[MCGP_NC][MCGP_LANES];      // compound_deg * (deg/0.05 if deg>0 else 1)   (:320-322)
     float opt[MCGP_NC][MCGP_LANES];          // pit window per compound, 0.85/1.1 scaled+truncated (:455-462)
-    float cdelta[MCGP_NC];                   // compound pace delta (:325)
+    float pc[MCGP_NC][MCGP_LANES];           // base_pace + compound pace delta (:325), rounded to FP32 once
     float grid[MCGP_LANES][MCGP_LANES];      // [pos][driver] qualifying probabilities
     uint8_t fixed_slot[MCGP_LANES];          // grid_fixed: grid slot of each driver
 };

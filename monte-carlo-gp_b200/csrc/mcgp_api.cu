@@ -70,6 +70,15 @@ static uint32_t prob_threshold(double p) {  // event iff 32-bit word < threshold
     return (uint32_t)floor(p * 4294967296.0);
 }
 
+// The per-lap test `u < rate` of src/simulation.py:194 makes a car's retirement lap geometric: lap = 2 + floor(ln u / ln(1 - rate)).
+static float dnf_scale(double rate) {
+    const double thr = (double)prob_threshold(rate) / 4294967296.0;  // same 2^-32 grid as every other probability
+    if (!(thr > 0.0)) return MCGP_DNF_NEVER;
+    if (thr >= 1.0 || rate >= 1.0) return -0.0f;
+    const float s = (float)(1.0 / log1p(-thr));
+    return s < -1e29f ? -1e29f : s;
+}
+
 static int validate(mcgp_handle h, const mcgp_race_params* r) {
     if (r->n_drivers < 1 || r->n_drivers > MCGP_MAX_DRIVERS) return fail(h, MCGP_EINVAL, "n_drivers must be in 1..32");
     if (r->total_laps < 1 || r->total_laps > 65535) return fail(h, MCGP_EINVAL, "total_laps must be in 1..65535");
@@ -104,19 +113,19 @@ static void derive_native(const mcgp_race_params* r, NativeRace* o) {
     o->red_thr = prob_threshold(r->red_flag_probability);
     o->sc_thr = prob_threshold(r->sc_probability);
     o->vsc_thr = prob_threshold(r->vsc_probability);
-    for (int c = 0; c < MCGP_NC; c++) o->cdelta[c] = (float)r->compound_pace_delta[c];
     for (int d = 0; d < MCGP_LANES; d++) {
         const bool car = d < n;
         o->pace[d] = car ? (float)r->base_pace[d] : 0.0f;
         o->deg_ovt[d] = car ? (float)r->tire_deg[d] : 0.0f;
         o->sigma[d] = car ? (float)r->driver_variance[d] : 0.0f;
-        o->dnf_thr[d] = car ? prob_threshold(r->dnf_rate[d]) : 0u;
+        o->dnf_scale[d] = car ? dnf_scale(r->dnf_rate[d]) : MCGP_DNF_NEVER;
         o->lap1_thr[d] = car ? prob_threshold(r->team_dnf_rate[d] * 4.0) : 0u;  // LAP_1_DNF_MULTIPLIER :282
         const double deg = car ? r->tire_deg[d] : 0.05;
         const double driver_factor = deg > 0 ? deg / 0.05 : 1.0;  // :321
         for (int c = 0; c < MCGP_NC; c++) {
             o->eff_deg[c][d] = car ? (float)(r->compound_deg_rate[c] * driver_factor) : 0.0f;
             o->opt[c][d] = car ? (float)pit_window(r, c, d) : 1e30f;
+            o->pc[c][d] = car ? (float)r->base_pace[d] + (float)r->compound_pace_delta[c] : 0.0f;
         }
     }
     for (int p = 0; p < MCGP_LANES; p++)

@@ -3,15 +3,23 @@
 // Behavioural source: reference src/simulation.py:59-560 (run_monte_carlo / simulate_race and the
 // handlers; each step below cites its lines).  What is B200-native here and absent upstream:
 //   * lane == driver index, so every per-driver parameter sits in a register for the whole launch;
-//   * draws come from Philox4x32-10 keyed by (seed; sim, lap, lane, stream): any sim range can be
-//     launched on any GPU in any order and gives the same counts;
+//   * draws come from Philox4x32-10 keyed by (seed; sim, lap pair, lane, stream): any sim range can be
+//     launched on any GPU in any order and gives the same counts.  One call per lane serves TWO laps
+//     (a Box-Muller pair + 2 x 3 overtake uniforms); the otherwise idle lanes 20..31 supply the extra
+//     words and the race-event draws, so no lane computes Philox for nothing;
+//   * a car's retirement lap is drawn once per race from the geometric law that the reference's per-lap
+//     test `u < dnf_rate` (:194) induces, instead of one test per driver-lap;
 //   * race times are FP32 *relative to the current leader* (re-based every lap in
 //     update_positions), which keeps ~1e-5 s resolution where absolute FP32 time would have 5e-4 s;
-//   * ordering = rank-by-counting over keys staged in shared memory (LDS.128 broadcast reads) plus
-//     an inverse permutation, so "car ahead" look-ups are single shuffles;
+//   * ordering: every car keeps its rank; a lap moves few cars far, so the new rank is the old one plus
+//     the crossings counted against the two old neighbours on each side, then VERIFIED (strictly sorted
+//     + a permutation) through a rank-indexed record array in shared memory; the rare misses fall back
+//     to rank-by-counting over all keys (LDS.128 broadcast reads).  The same records give each car its
+//     neighbour's time / overtake pace / last lap with one LDS.128 -- no inverse permutation;
 //   * overtakes: pair conditions and draws are evaluated in parallel in rank space, the sequential
 //     time re-write chain of :522-531 collapses to a closed form over runs of consecutive successes
-//     (one REDUX.OR ballot + bit scans);
+//     (one REDUX.OR + bit scans), and the order after a pass is the old one with each run reversed
+//     (verified with one neighbour compare);
 //   * the finish-position histogram accumulates in shared memory (uint32) and is flushed once per
 //     block with 64-bit global atomics.
 // The scalar CPU mirror of exactly this algorithm is oracle/native_mirror.c (test infrastructure).
@@ -33,6 +41,12 @@ constexpr unsigned FULL = 0xffffffffu;
 // VSC tyre-age rollback probability 0.3 (src/simulation.py:392) as a 32-bit threshold
 constexpr uint32_t kVscRollThr = 1288490188u;  // floor(0.3 * 2^32)
 
+// Ordering point between a warp's shared-memory writes and the reads of other lanes.  Every use below sits in
+// warp-convergent code (all loop bounds and branches are provably uniform), so it compiles to a scheduling fence
+// (a NOP), not a WARPSYNC.  An empty asm with a memory clobber is NOT enough: ptxas reorders a thread's LDS above
+// its own STS to a different address.
+#define WARP_FENCE() __syncwarp()
+
 // 1.0f iff a < b: a single FSET.BF on sm_100 (the integer-mask form costs FSETP + SEL)
 __device__ __forceinline__ float lt_one(float a, float b) {
     float m;
@@ -46,7 +60,7 @@ __device__ __forceinline__ float lt_one(float a, float b) {
 template <int NV4>
 __device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int n, uint32_t nmask) {
     S_t[lane] = t;  // lanes >= n pass +inf
-    __syncwarp();
+    WARP_FENCE();
     const float4* v4 = reinterpret_cast<const float4*>(S_t);
     const float4 v0 = v4[0];
     float c0 = lt_one(v0.x, t), c1 = lt_one(v0.y, t), c2 = lt_one(v0.z, t), c3 = lt_one(v0.w, t);
@@ -64,17 +78,17 @@ __device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int 
     if (seen != nmask) {
         for (int j = 0; j < lane; j++) cnt += (S_t[j] == t) ? 1 : 0;
     }
-    __syncwarp();
+    WARP_FENCE();
     return cnt;
 }
 
 struct Tables {  // per-lane view of the compound tables in shared memory
     const NativeRace* R;
     int lane;
-    __device__ __forceinline__ void load(int comp, float pace, float& eff, float& opt, float& pc) const {
+    __device__ __forceinline__ void load(int comp, float& eff, float& opt, float& pc) const {
         eff = R->eff_deg[comp][lane];
         opt = R->opt[comp][lane];
-        pc = __fadd_rn(pace, R->cdelta[comp]);
+        pc = R->pc[comp][lane];
     }
 };
 
@@ -93,13 +107,14 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                    const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
                    const __grid_constant__ NativeOutputs out) {
     constexpr bool kDetail = kOut >= 1, kTrace = kOut >= 2;
+    constexpr bool kSmall = NV4 == 5;  // n <= 20: lanes 20..31 carry no car and lend their Philox words
     uint8_t* __restrict__ finish = out.finish;
     float* __restrict__ times = out.times;
     __shared__ NativeRace R;
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     __shared__ __align__(16) float S_t_all[kWarpsPerBlock][32];
-    __shared__ uint32_t S_inv_all[kWarpsPerBlock][32];
-    __shared__ float S_w_all[kWarpsPerBlock][48];  // rank-indexed times with 8 pads of -inf below and +inf above
+    __shared__ float S_w_all[kWarpsPerBlock][48];              // window scratch: times by OLD rank, -inf / +inf pads
+    __shared__ __align__(16) float4 S_rec_all[kWarpsPerBlock][36];  // records by rank: {time, overtake pace, last lap, lane}
 
     const int race = blockIdx.y;
     {
@@ -113,23 +128,28 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     // warp-uniform values are broadcast from lane 0 so that the compiler can PROVE them uniform: every loop bound
     // and branch below is then convergent and the warp collectives need no divergence guards (BRA.DIV/WARPSYNC)
     const int lane = threadIdx.x & 31, warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
+    const float kInf = __int_as_float(0x7f800000), kNaN = __int_as_float(0x7fc00000);
     float* S_t = S_t_all[warp];
-    uint32_t* S_inv = S_inv_all[warp];
-    float* W = S_w_all[warp] + 8;  // W[-8..-1] = -inf, W[0..n) = times by rank, W[n..40) = +inf: no index guards needed
-    W[lane - 8] = lane < 8 ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
-    if (lane < 16) W[lane + 24] = __int_as_float(0x7f800000);
+    float* W = S_w_all[warp] + 8;   // W[-8..-1] = -inf, W[0..n) = times by rank, W[n..40) = +inf: no index guards needed
+    float4* REC = S_rec_all[warp] + 2;  // REC[-1] = {-inf, NaN, 0, -}: "no car ahead" blocks the pair and ends the order check
+    W[lane - 8] = lane < 8 ? -kInf : kInf;
+    if (lane < 16) W[lane + 24] = kInf;
+    if (lane < 2) REC[lane - 2] = make_float4(-kInf, kNaN, 0.0f, 0.0f);
     __syncwarp();
     const int n = __shfl_sync(FULL, R.n, 0), L = __shfl_sync(FULL, R.total_laps, 0), track = __shfl_sync(FULL, R.track, 0);
     const bool grid_fixed = __shfl_sync(FULL, R.grid_fixed, 0) != 0;
     const uint32_t nmask = n >= 32 ? FULL : ((1u << n) - 1u);
     const bool is_car = lane < n;
-    const float pace = R.pace[lane], deg_ovt = R.deg_ovt[lane], sigma = R.sigma[lane];
-    const uint32_t dnf_thr = R.dnf_thr[lane], lap1_thr = R.lap1_thr[lane];
-    const float pit_loss = R.pit_loss, ovt_delta = R.ovt_delta, drs_delta = R.drs_delta;
+    // overtake paces are carried pre-scaled by 2^15 (exact) so that the 16-bit uniform compares against them directly
+    const float pace32 = __fmul_rn(R.pace[lane], 32768.0f), deg32 = __fmul_rn(R.deg_ovt[lane], 32768.0f), sigma = R.sigma[lane];
+    const float dnf_scale = R.dnf_scale[lane];
+    const uint32_t lap1_thr = R.lap1_thr[lane];
+    const float pit_loss = R.pit_loss, drs_delta = R.drs_delta;
+    const float ovt32 = __fmul_rn(R.ovt_delta, 32768.0f), drs32_on = __fmul_rn(R.drs_delta, 32768.0f);
     const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
     const uint32_t red_thr = R.red_thr, sc_thr = R.sc_thr, vsc_thr = R.vsc_thr;
     const uint32_t stream = __shfl_sync(FULL, R.stream, 0);
-    const float kInf = __int_as_float(0x7f800000);
+    const int lend_lane = 20 + (lane < 10 ? lane : lane < 20 ? lane - 10 : 0);  // kSmall: whose spare words this lane borrows
     const Tables tab{&R, lane};
 
     const unsigned long long warps_per_race = (unsigned long long)gridDim.x * kWarpsPerBlock;
@@ -180,17 +200,23 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         else { comp = slot < 10 ? 0 : 1; age = slot < 10 ? 4.0f : 0.0f; }
         uint32_t used = 1u << comp;
         float eff, opt, pc;
-        tab.load(comp, pace, eff, opt, pc);
+        tab.load(comp, eff, opt, pc);
 
         // ---- _simulate_lap_1 (:275-311) --------------------------------------------------------
-        bool dnf;
-        int dnf_lap = 0;
+        // dnf_lap: the lap on which this car retires (0 on lanes without a car, > L: never).  Lap 1 uses 4 x the team
+        // rate (:286-287); from lap 2 on the per-lap test u < rate (:194) makes the retirement lap geometric.
+        int dnf_lap;
         float t, last = 0.0f, ahead_last = 0.0f;
         bool drs = false;
         {
             const uint4 w = philox4x32_10(sim_lo, sim_hi, (1u << 8) | (uint32_t)lane, stream, key);
-            dnf = !is_car || (w.x < lap1_thr);
-            if (is_car && dnf) dnf_lap = 1;
+            const float ug = __fmul_rn((float)(2u * (w.w >> 9) + 1u), 5.9604644775390625e-08f);  // (0,1), exact
+            float ln_u;
+            if (kExact) ln_u = exact_log(ug);
+            else { asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ln_u) : "f"(ug)); ln_u = __fmul_rn(ln_u, 0.6931471805599453f); }
+            dnf_lap = 2 + (int)(dnf_scale <= MCGP_DNF_NEVER ? 70000.0f : fminf(__fmul_rn(ln_u, dnf_scale), 70000.0f));
+            if (w.x < lap1_thr) dnf_lap = 1;
+            if (!is_car) dnf_lap = 0;
             float z1, z2;
             if (kExact) exact_normal2(w.y, w.z, z1, z2); else fast_normal2(w.y, w.z, z1, z2);
             float x = __fmaf_rn(age, eff, pc);
@@ -200,202 +226,76 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             if (slot < 3) sd = fminf(sd, 1.0f);
             const float lt = __fmaf_rn(-0.5f, sd, x);
             // retired on lap 1: distinct sentinel times below every runner; lanes without a car: +inf for good
-            t = !is_car ? kInf : dnf ? -(float)(lane + 1) : lt;
+            t = !is_car ? kInf : dnf_lap == 1 ? -(float)(lane + 1) : lt;
             age = __fadd_rn(age, 1.0f);
         }
 
         int drs_until = 0;
-        int rank = 0;
-        bool have_rank = false;  // warp-uniform: `rank` / S_inv describe the current times
+        int rank;
+        uint32_t bit;          // 1 << rank
+        float4 prev;           // record of the car one rank ahead (REC[rank - 1]), valid whenever have_rank
+        bool have_rank;        // warp-uniform: rank / bit / prev / REC describe the current times
         const bool traced = kTrace && s >= out.trace_first && s - out.trace_first < out.trace_count;
         int tr_event = 0;
         bool tr_pit = false;
 
-        // live cars' rank among the runners, derived on demand from the all-cars rank (events, classification)
-        auto live_position = [&]() -> int {
-            const uint32_t LM = __reduce_or_sync(FULL, !dnf ? (1u << rank) : 0u);
-            return __popc(LM & ((1u << rank) - 1u));
+        // all-cars rank by counting, then publish the records
+        auto full_rank = [&](float op32, bool dnf_now) {
+            rank = rank_by_count<NV4>(t, S_t, lane, n, nmask);
+            bit = 1u << (rank & 31);
+            if (is_car) REC[rank] = make_float4(t, dnf_now ? kNaN : op32, last, __int_as_float(lane));
+            WARP_FENCE();
+            prev = REC[rank - 1];
+            WARP_FENCE();
+            have_rank = true;
         };
-
-        for (int lap = 1; lap <= L; lap++) {
-            if (lap >= 2) {
-                const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, key);
-                const int rem = L - lap;
-                // ---- race-interrupting events (:168-176), decided on lane 31's words ------------
-                {
-                    uint4 we = w;
-                    if (n == 32) we = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 32u, stream, key);
-                    const bool any_ev = (we.x < red_thr) || (we.y < sc_thr) || (we.z < vsc_thr);
-                    if (__shfl_sync(FULL, (int)any_ev, 31)) {  // rare (2.7 % of laps with the product probabilities)
-                        const int code = (we.x < red_thr) ? 1 : (we.y < sc_thr) ? 2 : ((we.w < kVscRollThr) ? 4 : 3);
-                        const int ev = __shfl_sync(FULL, code, 31);
-                        const int pos_live = live_position();
-                        if (kTrace) tr_event = ev > 3 ? 3 : ev;
-                        if (ev == 1) {  // _handle_red_flag :397-431
-                            if (!dnf) {
-                                t = __fmul_rn(0.1f, (float)pos_live);
-                                age = 0.0f;
-                                comp = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
-                                used |= 1u << comp;
-                                tab.load(comp, pace, eff, opt, pc);
-                            }
-                            drs_until = lap + 2;
-                        } else if (ev == 2) {  // _handle_safety_car :334-376
-                            if (!dnf) {
-                                t = __fmul_rn(0.5f, (float)pos_live);
-                                age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
-                            }
-                            drs_until = lap + 2;
-                        } else {  // _handle_vsc :378-395
-                            if (!dnf) {
-                                t = __fmul_rn(t, 0.8f);
-                                if (ev == 4) age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
-                            }
-                            drs_until = lap + 1;
-                        }
-                    }
-                }
-
-                // ---- per-car lap (:186-223) ----------------------------------------------------
-                if (!dnf && w.x < dnf_thr) { dnf = true; dnf_lap = lap; }
-                float z, zunused;
-                if (kExact) exact_normal2(w.y, w.z, z, zunused); else z = fast_normal(w.y, w.z);
-                // _calculate_lap_time :313-332 (fuel is lap-uniform: every runner burns 1.5 kg per lap)
-                const float fuel_eff = __fmul_rn(fminf(110.0f, __fmul_rn(1.5f, (float)(lap - 1))), 0.03f);
-                const float fd = drs ? __fadd_rn(fuel_eff, drs_delta) : fuel_eff;
-                float x = __fmaf_rn(age, eff, pc);
-                x = __fadd_rn(x, -fd);
-                const float clean = __fmaf_rn(sigma, z, x);
-                float lt = clean;
-                if (t > 0.0f && ahead_last > 0.0f && t < dirty_thr)  // dirty air :208-216 (gap to the LEADER, Q3)
-                    lt = fmaxf(__fadd_rn(clean, dirty_pen), ahead_last);
-                if (!dnf) {
-                    t = __fadd_rn(t, lt);
-                    last = lt;
-                    age = __fadd_rn(age, 1.0f);
-                }
-
-                // ---- _handle_pit_stops (:433-494) ----------------------------------------------
-                const bool pit = !dnf && age > opt && rem > 5;
-                if (kTrace) tr_pit = pit;
-                if (__any_sync(FULL, pit)) {
-                    if (pit) {
-                        t = __fadd_rn(t, pit_loss);
-                        int nc = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
-                        const uint32_t ud = used & 7u;
-                        if (track == 0 && __popc(ud) == 1 && ((ud >> nc) & 1u)) {  // two-compound rule :481-488
-                            const uint32_t avail = 7u & ~ud;
-                            if (rem > 20) nc = (avail & 2u) ? 1 : R.pop_no_medium;
-                            else nc = (avail & 1u) ? 0 : R.pop_no_soft;
-                        }
-                        comp = nc;
-                        used |= 1u << comp;
-                        age = 0.0f;
-                        tab.load(comp, pace, eff, opt, pc);
-                    }
-                }
-
-                // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
-                const float op = dnf ? __int_as_float(0x7fc00000) : __fmaf_rn(age, deg_ovt, pace);  // NaN blocks the pair (Q5)
-                // First ordering of the lap.  `rank` still holds last lap's order; in 81 % of laps no car has moved more
-                // than two places, so count crossings against the two old neighbours on each side only, then verify
-                // (strictly sorted + a permutation) and fall back to the full 20-key count otherwise.
-                {
-                    if (is_car) W[rank] = t;
-                    __syncwarp();
-                    const float a1 = W[rank - 1], a2 = W[rank - 2], b1 = W[rank + 1], b2 = W[rank + 2];
-                    const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
-                    const int nr = rank + (int)moved;
-                    __syncwarp();
-                    if (is_car) { W[nr] = t; S_inv[nr] = lane; }
-                    __syncwarp();
-                    const bool bad = is_car && (!(W[nr - 1] < t) || (int)S_inv[nr] != lane);
-                    have_rank = !__any_sync(FULL, bad);
-                    if (have_rank) rank = nr;
-                    __syncwarp();
-                }
-#pragma unroll 1
-                for (int pass = 0; pass < 3; pass++) {
-                    if (!have_rank) {
-                        rank = rank_by_count<NV4>(t, S_t, lane, n, nmask);
-                        if (is_car) S_inv[rank] = lane;
-                        __syncwarp();
-                        have_rank = true;
-                    }
-                    const int la = (is_car && rank > 0) ? (int)S_inv[rank - 1] : lane;
-                    const float op_a = __shfl_sync(FULL, op, la);
-                    float delta = __fadd_rn(op_a, -op);
-                    if (drs) delta = __fadd_rn(delta, drs_delta);
-                    const uint32_t u16 = pass == 0 ? (w.w & 0xffffu) : pass == 1 ? (w.w >> 16) : (((w.y & 0xffu) << 8) | (w.z & 0xffu));
-                    // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling)
-                    const float thr = fminf(32768.0f, __fmul_rn(delta, 32768.0f));
-                    const bool succ = is_car && rank > 0 && delta > ovt_delta && (float)u16 < thr;
-                    const uint32_t M = __reduce_or_sync(FULL, succ ? (1u << rank) : 0u);
-                    if (M == 0u) break;
-                    // closed form of the sequential re-write chain :522-531 over runs of consecutive successes
-                    const uint32_t clear_below = ~M & ((2u << rank) - 1u);
-                    const int j = 31 - __clz(clear_below);  // run start (bit 0 of M is never set)
-                    const int k = rank - j;
-                    const int lj = is_car ? (int)S_inv[j] : lane;
-                    const float base = __shfl_sync(FULL, t, lj);
-                    const uint32_t above = ~((M >> rank) >> 1);  // bit i clear <=> pair (rank+i, rank+i+1) swapped
-                    const int sn = (int)(~above & 1u);
-                    if (is_car && (k + sn) > 0) {
-                        float v = __fmaf_rn(-0.1f, (float)(k + sn), base);
-                        if (sn) v = __fadd_rn(v, 0.3f);
-                        t = v;
-                    }
-                    // The new order is almost always the old one with every run [j, e] reversed (the re-written times
-                    // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
-                    // Verify the presumed order with one neighbour compare instead of re-counting all 20 ranks.
-                    const int e = rank + (__ffs(above) - 1);  // run end
-                    const int r2 = j + e - rank;
-                    __syncwarp();
-                    if (is_car) { W[r2] = t; S_inv[r2] = lane; }
-                    __syncwarp();
-                    const bool bad = is_car && !(W[r2 - 1] < t);
-                    have_rank = !__any_sync(FULL, bad);
-                    if (have_rank) rank = r2;
-                    __syncwarp();
-                }
+        // live cars' rank among the runners, derived on demand from the all-cars rank (events, classification)
+        auto live_position = [&](bool live) -> int {
+            const uint32_t LM = __reduce_or_sync(FULL, live ? bit : 0u);
+            return __popc(LM & (bit - 1u));
+        };
+        // _update_positions (:538-560), plus re-basing on the leader.  `prev` tells whether the car one rank ahead
+        // runs (its overtake pace is not NaN); the runner whose car ahead does not run is the leader, and when there
+        // is exactly one such runner every other runner's predecessor is simply the record already in `prev`.
+        auto update_positions = [&](const int lap, const bool dnf_now) {
+            const bool live = !dnf_now;
+            const bool pd = prev.y != prev.y;
+            const uint32_t B = __ballot_sync(FULL, live && pd);
+            bool has_pred;
+            float tl, t_pred, last_pred;
+            if (__popc(B) == 1) {
+                tl = __shfl_sync(FULL, t, __ffs(B) - 1);
+                has_pred = live && !pd;
+                t_pred = prev.x;
+                last_pred = prev.z;
+            } else if (B) {  // retired cars sit between runners (the lap of a retirement): search the live mask
+                const uint32_t LM = __reduce_or_sync(FULL, live ? bit : 0u);
+                tl = REC[__ffs(LM) - 1].x;
+                const uint32_t below = live ? (LM & (bit - 1u)) : 0u;
+                has_pred = below != 0u;
+                const float4 pr = REC[has_pred ? 31 - __clz(below) : 0];
+                t_pred = pr.x;
+                last_pred = pr.z;
+            } else {  // nobody left running: times stay as they are
+                return;
             }
-
-            // ---- _update_positions (:538-560), plus re-basing on the leader -----------------------
-            if (!have_rank) {
-                rank = rank_by_count<NV4>(t, S_t, lane, n, nmask);
-                if (is_car) S_inv[rank] = lane;
-                __syncwarp();
-                have_rank = true;
+            const bool drs_on = lap > 2 && lap > drs_until;
+            if (live) {
+                drs = has_pred && drs_on && (__fadd_rn(t, -t_pred) < 1.0f);
+                ahead_last = has_pred ? last_pred : 0.0f;
             }
-            {
-                const bool live = !dnf;
-                const uint32_t LM = __reduce_or_sync(FULL, live ? (1u << rank) : 0u);
-                if (LM) {
-                    const int lead_lane = (int)S_inv[__ffs(LM) - 1];
-                    const float tl = __shfl_sync(FULL, t, lead_lane);
-                    const uint32_t below = live ? (LM & ((1u << rank) - 1u)) : 0u;
-                    const bool has_pred = below != 0u;
-                    const int pl = has_pred ? (int)S_inv[31 - __clz(below)] : lane;
-                    const float t_pred = __shfl_sync(FULL, t, pl);
-                    const float last_pred = __shfl_sync(FULL, last, pl);
-                    const bool drs_on = lap > 2 && lap > drs_until;
-                    if (live) {
-                        drs = has_pred && drs_on && (__fadd_rn(t, -t_pred) < 1.0f);
-                        ahead_last = has_pred ? last_pred : 0.0f;
-                    }
-                    t = __fadd_rn(t, -tl);  // (+inf stays +inf on lanes without a car)
-                }
-                __syncwarp();
-            }
+            t = __fadd_rn(t, -tl);  // (+inf stays +inf on lanes without a car)
+        };
+        auto emit_trace = [&](const int lap, const bool dnf_now) {
             if (kTrace) {
                 if (traced) {  // one 8-byte record per driver per lap: 160 contiguous bytes per warp
-                    const int pl = live_position();
+                    const int pl = live_position(!dnf_now);
                     if (is_car) {
                         TraceRecord rec;
-                        rec.position = dnf ? 0 : (uint8_t)(pl + 1);
+                        rec.position = dnf_now ? 0 : (uint8_t)(pl + 1);
                         rec.compound = (uint8_t)comp;
                         rec.tire_age = (uint8_t)(int)age;
-                        rec.flags = (uint8_t)((dnf ? 1 : 0) | (drs ? 2 : 0) | (tr_pit ? 4 : 0) | (tr_event << 4));
+                        rec.flags = (uint8_t)((dnf_now ? 1 : 0) | (drs ? 2 : 0) | (tr_pit ? 4 : 0) | (tr_event << 4));
                         rec.gap = t;
                         out.trace[(((unsigned long long)race * out.trace_count + (s - out.trace_first)) * (unsigned)L + (unsigned)(lap - 1)) * (unsigned)n + lane] = rec;
                     }
@@ -403,8 +303,170 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 tr_event = 0;
                 tr_pit = false;
             }
+        };
+
+        full_rank(0.0f, dnf_lap <= 1);
+        update_positions(1, dnf_lap <= 1);
+        emit_trace(1, dnf_lap <= 1);
+
+        // One lap >= 2.  z: this lap's pace noise; u12: overtake uniforms of passes 1 / 2 in the low / high half;
+        // u3: pass 3 (16 bits); ev: the words that decide the race events, looked at on lane `ev_lane` only.
+        auto run_lap = [&](const int lap, const float z, const uint32_t u12, const uint32_t u3, const uint4 ev, const int ev_lane) {
+            const int rem = L - lap;
+            // ---- race-interrupting events (:168-176) ---------------------------------------------
+            {
+                const bool any_ev = lane == ev_lane && ((ev.x < red_thr) || (ev.y < sc_thr) || (ev.z < vsc_thr));
+                if (__any_sync(FULL, any_ev)) {  // rare (2.7 % of laps with the product probabilities)
+                    const int code = (ev.x < red_thr) ? 1 : (ev.y < sc_thr) ? 2 : ((ev.w < kVscRollThr) ? 4 : 3);
+                    const int e = __shfl_sync(FULL, code, ev_lane);
+                    const bool out_before = lap > dnf_lap;  // retired on an earlier lap (this lap's retirements still run here)
+                    const int pos_live = live_position(!out_before);
+                    if (kTrace) tr_event = e > 3 ? 3 : e;
+                    if (e == 1) {  // _handle_red_flag :397-431
+                        if (!out_before) {
+                            t = __fmul_rn(0.1f, (float)pos_live);
+                            age = 0.0f;
+                            comp = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
+                            used |= 1u << comp;
+                            tab.load(comp, eff, opt, pc);
+                        }
+                        drs_until = lap + 2;
+                    } else if (e == 2) {  // _handle_safety_car :334-376
+                        if (!out_before) {
+                            t = __fmul_rn(0.5f, (float)pos_live);
+                            age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
+                        }
+                        drs_until = lap + 2;
+                    } else {  // _handle_vsc :378-395
+                        if (!out_before) {
+                            t = __fmul_rn(t, 0.8f);
+                            if (e == 4) age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
+                        }
+                        drs_until = lap + 1;
+                    }
+                }
+            }
+
+            // ---- per-car lap (:186-223) --------------------------------------------------------
+            const bool dnf = lap >= dnf_lap;
+            // _calculate_lap_time :313-332 (fuel is lap-uniform: every runner burns 1.5 kg per lap)
+            const float fuel_eff = __fmul_rn(fminf(110.0f, __fmul_rn(1.5f, (float)(lap - 1))), 0.03f);
+            const float fd = drs ? __fadd_rn(fuel_eff, drs_delta) : fuel_eff;
+            float x = __fmaf_rn(age, eff, pc);
+            x = __fadd_rn(x, -fd);
+            const float clean = __fmaf_rn(sigma, z, x);
+            float lt = clean;
+            if (t > 0.0f && ahead_last > 0.0f && t < dirty_thr)  // dirty air :208-216 (gap to the LEADER, Q3)
+                lt = fmaxf(__fadd_rn(clean, dirty_pen), ahead_last);
+            if (!dnf) {
+                t = __fadd_rn(t, lt);
+                last = lt;
+                age = __fadd_rn(age, 1.0f);
+            }
+
+            // ---- _handle_pit_stops (:433-494) ----------------------------------------------
+            const bool pit = !dnf && age > opt && rem > 5;
+            if (kTrace) tr_pit = pit;
+            if (__any_sync(FULL, pit)) {
+                if (pit) {
+                    t = __fadd_rn(t, pit_loss);
+                    int nc = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
+                    const uint32_t ud = used & 7u;
+                    if (track == 0 && __popc(ud) == 1 && ((ud >> nc) & 1u)) {  // two-compound rule :481-488
+                        const uint32_t avail = 7u & ~ud;
+                        if (rem > 20) nc = (avail & 2u) ? 1 : R.pop_no_medium;
+                        else nc = (avail & 1u) ? 0 : R.pop_no_soft;
+                    }
+                    comp = nc;
+                    used |= 1u << comp;
+                    age = 0.0f;
+                    tab.load(comp, eff, opt, pc);
+                }
+            }
+
+            // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
+            // overtake pace (x 2^15); NaN for a retired car blocks both pairs it sits in (Q5)
+            const float op32 = dnf ? kNaN : __fmaf_rn(age, deg32, pace32);
+            const float opb = drs ? __fadd_rn(op32, -drs32_on) : op32;  // as the chasing car: DRS helps (:517-518)
+            // First ordering of the lap.  `rank` still holds last lap's order; in 4 laps of 5 no car has moved more
+            // than two places, so count crossings against the two old neighbours on each side only, then verify
+            // (strictly sorted + a permutation) and fall back to the full count otherwise.
+            {
+                if (is_car) W[rank] = t;
+                WARP_FENCE();
+                const float a1 = W[rank - 1], a2 = W[rank - 2], b1 = W[rank + 1], b2 = W[rank + 2];
+                const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
+                const int nr = rank + (int)moved;
+                const uint32_t nbit = 1u << (nr & 31);
+                WARP_FENCE();
+                if (is_car) REC[nr] = make_float4(t, op32, last, __int_as_float(lane));
+                const uint32_t cover = __reduce_or_sync(FULL, is_car ? nbit : 0u);
+                WARP_FENCE();
+                const float4 pv = REC[nr - 1];
+                const bool bad = is_car && !(pv.x < t);
+                have_rank = cover == nmask && !__any_sync(FULL, bad);
+                if (have_rank) { rank = nr; bit = nbit; prev = pv; }
+                WARP_FENCE();
+            }
+#pragma unroll 1
+            for (int pass = 0; pass < 3; pass++) {
+                if (!have_rank) full_rank(op32, dnf);
+                const float delta = __fadd_rn(prev.y, -opb);  // pace_ahead - pace_behind (+ drs_delta), x 2^15
+                const uint32_t u16 = pass == 0 ? (u12 & 0xffffu) : pass == 1 ? (u12 >> 16) : u3;
+                // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling)
+                const bool succ = delta > ovt32 && (float)u16 < fminf(32768.0f, delta);
+                const uint32_t M = __reduce_or_sync(FULL, succ ? bit : 0u);
+                if (M == 0u) break;
+                // closed form of the sequential re-write chain :522-531 over runs of consecutive successes: with j the
+                // run start, k = rank - j and sn = "the car behind me succeeds too", the car ends on
+                // T[j] - 0.1 (k + sn) + 0.3 sn = T[j] - 0.1 (k - 2 sn); a car outside every run has k = sn = 0.
+                const uint32_t clear_below = ~M & ((bit << 1) - 1u);
+                const int j = 31 - __clz(clear_below);  // run start (bit 0 of M is never set)
+                const uint32_t above = ~((M >> rank) >> 1);  // bit i clear <=> pair (rank+i, rank+i+1) swapped
+                const int sn = (int)(~above & 1u);
+                const float base = REC[j].x;
+                if (is_car) t = __fmaf_rn(-0.1f, (float)(rank - j - 2 * sn), base);
+                // The new order is almost always the old one with every run [j, e] reversed (the re-written times
+                // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
+                // Verify the presumed order with one neighbour compare instead of re-counting all ranks.
+                const int r2 = j + (__ffs(above) - 1);  // j + e - rank with e = rank + ffs(above) - 1 the run end
+                WARP_FENCE();
+                if (is_car) REC[r2] = make_float4(t, op32, last, __int_as_float(lane));
+                WARP_FENCE();
+                const float4 pv = REC[r2 - 1];
+                const bool bad = is_car && !(pv.x < t);
+                have_rank = !__any_sync(FULL, bad);
+                if (have_rank) { rank = r2; bit = 1u << (r2 & 31); prev = pv; }
+                WARP_FENCE();
+            }
+            if (!have_rank) full_rank(op32, dnf);
+            update_positions(lap, dnf);
+            emit_trace(lap, dnf);
+        };
+
+        for (int lap = 2; lap <= L; lap += 2) {
+            // one Philox call per lane per lap PAIR: x, y -> Box-Muller pair (cos: this lap, sin: the next);
+            // z -> this lap's overtake passes 1, 2; w -> the next lap's; passes 3 come from a borrowed word
+            const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, key);
+            uint32_t extra;
+            uint4 ev0, ev1;
+            if (kSmall) {  // lanes 20..29 lend x (to drivers 0..9) and y (to drivers 10..19); lanes 31 / 30 decide the events
+                const uint32_t e1 = __shfl_sync(FULL, w.x, lend_lane), e2 = __shfl_sync(FULL, w.y, lend_lane);
+                extra = lane < 10 ? e1 : e2;
+                ev0 = w;
+                ev1 = w;
+            } else {  // up to 32 cars: a second call per lane, and two warp-uniform calls for the events
+                extra = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)(lane + 32), stream, key).x;
+                ev0 = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 64u, stream, key);
+                ev1 = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 65u, stream, key);
+            }
+            float za, zb;
+            if (kExact) exact_normal2(w.x, w.y, za, zb); else fast_normal2(w.x, w.y, za, zb);
+            run_lap(lap, za, w.z, extra & 0xffffu, ev0, 31);
+            if (lap + 1 <= L) run_lap(lap + 1, zb, w.w, extra >> 16, ev1, 30);
         }
-        const int pos_live = live_position();
+        const bool dnf = L >= dnf_lap;
+        const int pos_live = live_position(!dnf);
 
         // ---- final classification (:231-242) -----------------------------------------------------
         {
@@ -417,7 +479,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 const int jl = __shfl_sync(FULL, dnf_lap, j);
                 const float jt = __shfl_sync(FULL, tc, j);
                 const int js = __shfl_sync(FULL, slot, j);
-                const bool jd = __shfl_sync(FULL, (int)dnf, j) != 0;
+                const bool jd = jl <= L;
                 const bool ahead = jd && j != lane &&
                                    (jl > dnf_lap || (jl == dnf_lap && (jt > tc || (jt == tc && js < slot))));
                 worse += ahead ? 1 : 0;

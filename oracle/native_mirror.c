@@ -4,14 +4,18 @@
  * statistically.  To still check its *logic* exactly, this file restates the native algorithm the plain
  * way -- one car at a time, full sorts, no warp tricks -- following the reference's structure
  * (src/simulation.py:102-560, cited per function) with the native arithmetic:
- *   - draws: Philox4x32-10, key = seed, counter = (sim, lap<<8 | driver, stream)
- *       lap 0  word0 of "driver" p      -> grid position p's uniform
- *       lap 1  word0 lap-1 DNF; words 1,2 -> Box-Muller pair (cos: pace noise, sin: start delta)
- *       lap>=2 word0 DNF; words 1,2 (top 24 bits) -> pace noise; word3 lo/hi 16 -> overtake pass 1/2;
- *              low 8 bits of words 1,2 -> overtake pass 3; "driver" 31 (32 if n == 32): words 0..3 ->
- *              red / SC / VSC / VSC tyre roll-back
+ *   - draws: Philox4x32-10, key = seed, counter = (sim, lap<<8 | lane, stream)
+ *       lap 0  word0 of lane p          -> grid position p's uniform
+ *       lap 1  word0 lap-1 DNF; words 1,2 -> Box-Muller pair (cos: pace noise, sin: start delta);
+ *              word3 (top 23 bits) -> the retirement lap >= 2, geometric: 2 + floor(ln u / ln(1 - rate))
+ *       laps (l, l+1), l even: ONE call per lane: words 0,1 (top 24 bits) -> Box-Muller pair (cos: lap l,
+ *              sin: lap l+1); word2 lo/hi 16 -> lap l overtake pass 1/2; word3 -> the same for lap l+1;
+ *              pass 3 of laps l / l+1 = lo / hi 16 bits of a borrowed word: n <= 20: word0 of lane 20+d (d < 10)
+ *              or word1 of lane 10+d (d >= 10); n > 20: word0 of lane 32+d.
+ *              events (red / SC / VSC / VSC tyre roll-back = words 0..3): n <= 20: lane 31 for lap l, lane 30
+ *              for lap l+1; n > 20: lanes 64 / 65
  *   - FP32, every fused op explicit (fmaf), times re-based on the leader after every lap,
- *     overtake chains in closed form  base - 0.1*k (+0.3), ordering by (time, driver index).
+ *     overtake chains in closed form  base - 0.1*(k - 2*sn), ordering by (time, driver index).
  * With the "exact" normal generator (IEEE-only arithmetic) kernel and mirror agree bit for bit; the
  * mirror itself is checked statistically against the FP64 oracle (tests/test_native_mirror.py).
  * Build flags: -ffp-contract=off (oracle/Makefile). */
@@ -98,11 +102,20 @@ static uint32_t prob_threshold(double p) {
     return (uint32_t)floor(p * 4294967296.0);
 }
 
+#define DNF_NEVER (-1e30f)
+static float dnf_scale(double rate) { /* 1 / ln(1 - rate) on the 2^-32 probability grid */
+    const double thr = (double)prob_threshold(rate) / 4294967296.0;
+    if (!(thr > 0.0)) return DNF_NEVER;
+    if (thr >= 1.0 || rate >= 1.0) return -0.0f;
+    const float s = (float)(1.0 / log1p(-thr));
+    return s < -1e29f ? -1e29f : s;
+}
+
 #define N32 32
 typedef struct {
     int n, L, track;
-    float pace[N32], deg_ovt[N32], sigma[N32], eff[5][N32], opt[5][N32], cdelta[5], G[N32][N32];
-    uint32_t dnf_thr[N32], lap1_thr[N32], red_thr, sc_thr, vsc_thr;
+    float pace[N32], deg_ovt[N32], sigma[N32], eff[5][N32], opt[5][N32], pc[5][N32], dnf_scale[N32], G[N32][N32];
+    uint32_t lap1_thr[N32], red_thr, sc_thr, vsc_thr;
     float pit_loss, ovt_delta, drs_delta, dirty_thr, dirty_pen;
     int grid_fixed, fixed_slot[N32];
 } nat_t;
@@ -114,10 +127,9 @@ static void derive(const orc_params* p, nat_t* o) {
     o->pit_loss = (float)p->pit_loss; o->ovt_delta = (float)p->overtake_delta; o->drs_delta = (float)p->drs_delta;
     o->dirty_thr = (float)p->dirty_thr; o->dirty_pen = (float)p->dirty_pen;
     o->red_thr = prob_threshold(p->red_p); o->sc_thr = prob_threshold(p->sc_p); o->vsc_thr = prob_threshold(p->vsc_p);
-    for (int c = 0; c < 5; c++) o->cdelta[c] = (float)p->compound_pace_delta[c];
     for (int d = 0; d < n; d++) {
         o->pace[d] = (float)p->base_pace[d]; o->deg_ovt[d] = (float)p->tire_deg[d]; o->sigma[d] = (float)p->variance[d];
-        o->dnf_thr[d] = prob_threshold(p->dnf_rate[d]);
+        o->dnf_scale[d] = dnf_scale(p->dnf_rate[d]);
         o->lap1_thr[d] = prob_threshold(p->team_rate[d] * 4.0);
         double deg = p->tire_deg[d], factor = deg > 0 ? deg / 0.05 : 1.0;
         for (int c = 0; c < 5; c++) {
@@ -125,6 +137,7 @@ static void derive(const orc_params* p, nat_t* o) {
             double optimal = p->compound_optimal[c], dd = p->tire_deg_pit[d];
             if (dd > 0.05) optimal = trunc(optimal * 0.85); else if (dd < 0.02) optimal = trunc(optimal * 1.1);
             o->opt[c][d] = (float)optimal;
+            o->pc[c][d] = (float)p->base_pace[d] + (float)p->compound_pace_delta[c];
         }
         for (int pos = 0; pos < n; pos++)
             o->G[pos][d] = p->grid_kind[d][pos] != ORC_ITEM_INT0 ? (float)p->grid_probs[d][pos] : 0.0f;
@@ -148,7 +161,7 @@ typedef struct {
 } ncar;
 
 static void load_tables(const nat_t* R, ncar* c, int d) {
-    c->eff = R->eff[c->comp][d]; c->opt = R->opt[c->comp][d]; c->pc = R->pace[d] + R->cdelta[c->comp];
+    c->eff = R->eff[c->comp][d]; c->opt = R->opt[c->comp][d]; c->pc = R->pc[c->comp][d];
 }
 
 /* all cars ordered by (time, driver index) -- what every sorted() of the reference becomes */
@@ -250,8 +263,14 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
             else { c->comp = c->slot < 10 ? 0 : 1; c->age = c->slot < 10 ? 4.0f : 0.0f; }
             c->used = 1u << c->comp;
             load_tables(&R, c, d);
-            c->last = 0.0f; c->ahead_last = 0.0f; c->drs = 0; c->pos_live = 0; c->dnf_lap = 0;
+            c->last = 0.0f; c->ahead_last = 0.0f; c->drs = 0; c->pos_live = 0;
             u4 ww = philox(s0, s1, (1u << 8) | (uint32_t)d, stream, k0, k1);
+            {
+                const float ug = (float)(2u * (ww.w >> 9) + 1u) * 5.9604644775390625e-08f;
+                const float ln_u = exact ? exact_log(ug) : logf(ug);
+                const float xl = R.dnf_scale[d] <= DNF_NEVER ? 70000.0f : fminf(ln_u * R.dnf_scale[d], 70000.0f);
+                c->dnf_lap = 2 + (int)xl;
+            }
             c->dnf = ww.x < R.lap1_thr[d];
             if (c->dnf) c->dnf_lap = 1;
             float z1, z2;
@@ -270,9 +289,12 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
         memset(pitted, 0, sizeof(pitted));
         emit_trace(trace, s, L, n, 1, cars, pitted, 0);
 
+        float zn[N32];   /* the second Box-Muller variate, kept for the odd lap of the pair */
+        uint32_t u12[N32], u3[N32];
         for (int lap = 2; lap <= L; lap++) {
+            const uint32_t pair = (uint32_t)(lap & ~1), odd = (uint32_t)(lap & 1);
             /* ---- events :168-176 ---- */
-            u4 we = philox(s0, s1, ((uint32_t)lap << 8) | (n == 32 ? 32u : 31u), stream, k0, k1);
+            u4 we = philox(s0, s1, (pair << 8) | (n <= 20 ? 31u - odd : 64u + odd), stream, k0, k1);
             const int ev = we.x < R.red_thr ? 1 : we.y < R.sc_thr ? 2 : we.z < R.vsc_thr ? (we.w < 1288490188u ? 4 : 3) : 0;
             const int rem = L - lap;
             const int nc_rule = R.track == 2 ? 4 : R.track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
@@ -296,11 +318,22 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
             const float fuel_eff = fminf(110.0f, 1.5f * (float)(lap - 1)) * 0.03f;
             for (int d = 0; d < n; d++) {
                 ncar* c = &cars[d];
-                w[d] = philox(s0, s1, ((uint32_t)lap << 8) | (uint32_t)d, stream, k0, k1);
+                const uint32_t extra = n <= 20 ? (d < 10 ? philox(s0, s1, (pair << 8) | (uint32_t)(20 + d), stream, k0, k1).x
+                                                         : philox(s0, s1, (pair << 8) | (uint32_t)(10 + d), stream, k0, k1).y)
+                                               : philox(s0, s1, (pair << 8) | (uint32_t)(32 + d), stream, k0, k1).x;
+                float z;
+                if (!odd) {
+                    w[d] = philox(s0, s1, (pair << 8) | (uint32_t)d, stream, k0, k1);
+                    normal2(exact, w[d].x, w[d].y, &z, &zn[d]);
+                    u12[d] = w[d].z;
+                    u3[d] = extra & 0xffffu;
+                } else {
+                    z = zn[d];
+                    u12[d] = w[d].w;
+                    u3[d] = extra >> 16;
+                }
                 if (c->dnf) continue;
-                if (w[d].x < R.dnf_thr[d]) { c->dnf = 1; c->dnf_lap = lap; continue; }
-                float z, zb;
-                normal2(exact, w[d].y, w[d].z, &z, &zb);
+                if (lap >= c->dnf_lap) { c->dnf = 1; continue; }
                 const float fd = c->drs ? fuel_eff + R.drs_delta : fuel_eff;
                 float x = fmaf(c->age, c->eff, c->pc);
                 x = x + -fd;
@@ -330,7 +363,8 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
             }
             /* ---- _simulate_overtakes :496-536 ---- */
             float op[N32];
-            for (int d = 0; d < n; d++) op[d] = cars[d].dnf ? NAN : fmaf(cars[d].age, R.deg_ovt[d], R.pace[d]);
+            /* paces x 2^15 (exact scaling): the 16-bit uniform then compares against delta directly */
+            for (int d = 0; d < n; d++) op[d] = cars[d].dnf ? NAN : fmaf(cars[d].age, R.deg_ovt[d] * 32768.0f, R.pace[d] * 32768.0f);
             for (int pass = 0; pass < 3; pass++) {
                 int ord[N32], succ[N32 + 1], any = 0;
                 float T[N32];
@@ -339,13 +373,11 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
                 for (int r = 0; r < n; r++) T[r] = cars[ord[r]].t;
                 for (int r = 1; r < n; r++) {
                     const int b = ord[r], a = ord[r - 1];
-                    float delta = op[a] + -op[b];
-                    if (cars[b].drs) delta = delta + R.drs_delta;
-                    const uint32_t u16 = pass == 0 ? (w[b].w & 0xffffu) : pass == 1 ? (w[b].w >> 16)
-                                                   : (((w[b].y & 0xffu) << 8) | (w[b].z & 0xffu));
-                    const float u = (float)u16 * 1.52587890625e-05f;
-                    const float prob = fminf(0.5f, delta * 0.5f);
-                    succ[r] = delta > R.ovt_delta && u < prob;
+                    const float opb = cars[b].drs ? op[b] + -(R.drs_delta * 32768.0f) : op[b];
+                    const float delta = op[a] + -opb;
+                    const uint32_t u16 = pass == 0 ? (u12[b] & 0xffffu) : pass == 1 ? (u12[b] >> 16) : u3[b];
+                    /* u16 * 2^-16 < min(0.5, delta / 2), both sides x 2^16 */
+                    succ[r] = delta > R.ovt_delta * 32768.0f && (float)u16 < fminf(32768.0f, delta);
                     any |= succ[r];
                 }
                 if (!any) break;
@@ -353,11 +385,7 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
                     int k = 0;
                     while (succ[r - k]) k++; /* succ[0] == 0 stops the scan */
                     const int sn = succ[r + 1];
-                    if (k + sn > 0) {
-                        float v = fmaf(-0.1f, (float)(k + sn), T[r - k]);
-                        if (sn) v = v + 0.3f;
-                        cars[ord[r]].t = v;
-                    }
+                    if (k + sn > 0) cars[ord[r]].t = fmaf(-0.1f, (float)(k - 2 * sn), T[r - k]);
                 }
             }
             update_positions(cars, n, lap, drs_until);
