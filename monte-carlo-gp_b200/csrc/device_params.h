@@ -18,7 +18,7 @@ struct NativeRace {
     int32_t grid_fixed;   // 1: grid_probs is a deterministic permutation, fixed_slot[] is the grid
     int32_t _pad;
     float pit_loss, ovt_delta, drs_delta, dirty_thr, dirty_pen;
-    uint32_t red_thr, sc_thr, vsc_thr;       // floor(p * 2^32), event iff word < thr
+    uint32_t red_thr, sc_thr, vsc_thr;       // CUMULATIVE floor(P * 2^32): red if w < red_thr, else SC if w < sc_thr, else VSC if w < vsc_thr
     float pace[MCGP_LANES];                  // base_pace
     float deg_ovt[MCGP_LANES];               // raw tire_deg (overtake pace, src/simulation.py:514)
     float sigma[MCGP_LANES];                 // driver_variance

@@ -79,6 +79,8 @@ static float dnf_scale(double rate) {
     return s < -1e29f ? -1e29f : s;
 }
 
+static double clamp01(double p) { return !(p > 0.0) ? 0.0 : p > 1.0 ? 1.0 : p; }
+
 static int validate(mcgp_handle h, const mcgp_race_params* r) {
     if (r->n_drivers < 1 || r->n_drivers > MCGP_MAX_DRIVERS) return fail(h, MCGP_EINVAL, "n_drivers must be in 1..32");
     if (r->total_laps < 1 || r->total_laps > 65535) return fail(h, MCGP_EINVAL, "total_laps must be in 1..65535");
@@ -110,9 +112,14 @@ static void derive_native(const mcgp_race_params* r, NativeRace* o) {
     o->pop_no_medium = r->pop_no_medium; o->pop_no_soft = r->pop_no_soft; o->stream = r->stream;
     o->pit_loss = (float)r->pit_loss; o->ovt_delta = (float)r->overtake_delta; o->drs_delta = (float)r->drs_delta;
     o->dirty_thr = (float)r->dirty_air_threshold; o->dirty_pen = (float)r->dirty_air_penalty;
-    o->red_thr = prob_threshold(r->red_flag_probability);
-    o->sc_thr = prob_threshold(r->sc_probability);
-    o->vsc_thr = prob_threshold(r->vsc_probability);
+    {   // red flag, else SC, else VSC (:168-176): one draw against the cumulative probabilities
+        const double pr = clamp01(r->red_flag_probability), ps = clamp01(r->sc_probability), pv = clamp01(r->vsc_probability);
+        o->red_thr = prob_threshold(pr);
+        o->sc_thr = prob_threshold(pr + (1.0 - pr) * ps);
+        o->vsc_thr = prob_threshold(pr + (1.0 - pr) * (ps + (1.0 - ps) * pv));
+        if (o->sc_thr < o->red_thr) o->sc_thr = o->red_thr;
+        if (o->vsc_thr < o->sc_thr) o->vsc_thr = o->sc_thr;
+    }
     for (int d = 0; d < MCGP_LANES; d++) {
         const bool car = d < n;
         o->pace[d] = car ? (float)r->base_pace[d] : 0.0f;

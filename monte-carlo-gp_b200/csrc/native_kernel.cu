@@ -38,14 +38,40 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned FULL = 0xffffffffu;
 
-// VSC tyre-age rollback probability 0.3 (src/simulation.py:392) as a 32-bit threshold
-constexpr uint32_t kVscRollThr = 1288490188u;  // floor(0.3 * 2^32)
+// VSC tyre-age rollback probability 0.3 (src/simulation.py:392) as a 16-bit threshold
+constexpr uint32_t kVscRoll16 = 19660u;  // floor(0.3 * 2^16)
 
 // Ordering point between a warp's shared-memory writes and the reads of other lanes.  Every use below sits in
 // warp-convergent code (all loop bounds and branches are provably uniform), so it compiles to a scheduling fence
 // (a NOP), not a WARPSYNC.  An empty asm with a memory clobber is NOT enough: ptxas reorders a thread's LDS above
 // its own STS to a different address.
 #define WARP_FENCE() __syncwarp()
+
+// Shared-memory accessors on 32-bit shared addresses.  `volatile` keeps ptxas from reordering a lane's LDS above
+// its own STS to another address (which it otherwise does: the two never alias for ONE thread), so inside
+// warp-convergent code -- where a warp's LDS/STS issue in program order -- they need no __syncwarp() between
+// them (that would compile to a NOP, but a NOP still costs an issue slot).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ float lds_f(uint32_t a) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f(uint32_t a, float v) {
+    asm volatile("st.volatile.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.volatile.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 
 // 1.0f iff a < b: a single FSET.BF on sm_100 (the integer-mask form costs FSETP + SEL)
 __device__ __forceinline__ float lt_one(float a, float b) {
@@ -136,6 +162,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     if (lane < 16) W[lane + 24] = kInf;
     if (lane < 2) REC[lane - 2] = make_float4(-kInf, kNaN, 0.0f, 0.0f);
     __syncwarp();
+    const uint32_t w_sh = smem_u32(W), rec_sh = smem_u32(REC);
     const int n = __shfl_sync(FULL, R.n, 0), L = __shfl_sync(FULL, R.total_laps, 0), track = __shfl_sync(FULL, R.track, 0);
     const bool grid_fixed = __shfl_sync(FULL, R.grid_fixed, 0) != 0;
     const uint32_t nmask = n >= 32 ? FULL : ((1u << n) - 1u);
@@ -147,7 +174,10 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     const float pit_loss = R.pit_loss, drs_delta = R.drs_delta;
     const float ovt32 = __fmul_rn(R.ovt_delta, 32768.0f), drs32_on = __fmul_rn(R.drs_delta, 32768.0f);
     const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
-    const uint32_t red_thr = R.red_thr, sc_thr = R.sc_thr, vsc_thr = R.vsc_thr;
+    // cumulative event thresholds (red | SC | VSC share one draw); only the event lane ever sees a non-zero ev_any
+    const int ev_lane = kSmall ? 31 : 0;
+    const uint32_t red_thr = R.red_thr, sc_thr = R.sc_thr;
+    const uint32_t ev_any = (!kSmall || lane == ev_lane) ? R.vsc_thr : 0u;
     const uint32_t stream = __shfl_sync(FULL, R.stream, 0);
     const int lend_lane = 20 + (lane < 10 ? lane : lane < 20 ? lane - 10 : 0);  // kSmall: whose spare words this lane borrows
     const Tables tab{&R, lane};
@@ -207,7 +237,6 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         // rate (:286-287); from lap 2 on the per-lap test u < rate (:194) makes the retirement lap geometric.
         int dnf_lap;
         float t, last = 0.0f, ahead_last = 0.0f;
-        bool drs = false;
         {
             const uint4 w = philox4x32_10(sim_lo, sim_hi, (1u << 8) | (uint32_t)lane, stream, key);
             const float ug = __fmul_rn((float)(2u * (w.w >> 9) + 1u), 5.9604644775390625e-08f);  // (0,1), exact
@@ -233,20 +262,26 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         int drs_until = 0;
         int rank;
         uint32_t bit;          // 1 << rank
+        uint32_t wa, ra;       // shared addresses of W[rank] and REC[rank]
         float4 prev;           // record of the car one rank ahead (REC[rank - 1]), valid whenever have_rank
-        bool have_rank;        // warp-uniform: rank / bit / prev / REC describe the current times
+        bool have_rank;        // warp-uniform: rank / bit / wa / ra / prev / REC describe the current times
+        float drs_f = 0.0f, drs32 = 0.0f;  // drs_delta (and x 2^15) while DRS is enabled for this car, else 0
+        float fuel = 0.0f;     // (110 - fuel_load) * 0.03 of the current lap: every runner burns 1.5 kg per lap (:221, Q11)
         const bool traced = kTrace && s >= out.trace_first && s - out.trace_first < out.trace_count;
         int tr_event = 0;
-        bool tr_pit = false;
+        bool tr_pit = false, tr_drs = false;
 
+        auto set_rank = [&](int r) {
+            rank = r;
+            bit = 1u << (r & 31);
+            wa = w_sh + 4u * (uint32_t)r;
+            ra = rec_sh + 16u * (uint32_t)r;
+        };
         // all-cars rank by counting, then publish the records
-        auto full_rank = [&](float op32, bool dnf_now) {
-            rank = rank_by_count<NV4>(t, S_t, lane, n, nmask);
-            bit = 1u << (rank & 31);
-            if (is_car) REC[rank] = make_float4(t, dnf_now ? kNaN : op32, last, __int_as_float(lane));
-            WARP_FENCE();
-            prev = REC[rank - 1];
-            WARP_FENCE();
+        auto full_rank = [&](float op32) {
+            set_rank(rank_by_count<NV4>(t, S_t, lane, n, nmask));
+            if (is_car) sts_f4<0>(ra, t, op32, last, 0.0f);
+            prev = lds_f4<-16>(ra);
             have_rank = true;
         };
         // live cars' rank among the runners, derived on demand from the all-cars rank (events, classification)
@@ -261,29 +296,26 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             const bool live = !dnf_now;
             const bool pd = prev.y != prev.y;
             const uint32_t B = __ballot_sync(FULL, live && pd);
-            bool has_pred;
-            float tl, t_pred, last_pred;
+            bool has_pred = live && !pd;
+            float tl, t_pred = prev.x, last_pred = prev.z;
             if (__popc(B) == 1) {
-                tl = __shfl_sync(FULL, t, __ffs(B) - 1);
-                has_pred = live && !pd;
-                t_pred = prev.x;
-                last_pred = prev.z;
+                tl = __shfl_sync(FULL, t, 31 - __clz(B));
             } else if (B) {  // retired cars sit between runners (the lap of a retirement): search the live mask
                 const uint32_t LM = __reduce_or_sync(FULL, live ? bit : 0u);
-                tl = REC[__ffs(LM) - 1].x;
+                tl = lds_f<0>(rec_sh + 16u * (uint32_t)(__ffs(LM) - 1));
                 const uint32_t below = live ? (LM & (bit - 1u)) : 0u;
                 has_pred = below != 0u;
-                const float4 pr = REC[has_pred ? 31 - __clz(below) : 0];
+                const float4 pr = lds_f4<0>(rec_sh + 16u * (uint32_t)(has_pred ? 31 - __clz(below) : 0));
                 t_pred = pr.x;
                 last_pred = pr.z;
             } else {  // nobody left running: times stay as they are
                 return;
             }
-            const bool drs_on = lap > 2 && lap > drs_until;
-            if (live) {
-                drs = has_pred && drs_on && (__fadd_rn(t, -t_pred) < 1.0f);
-                ahead_last = has_pred ? last_pred : 0.0f;
-            }
+            const bool drs_now = has_pred && lap > 2 && lap > drs_until && (__fadd_rn(t, -t_pred) < 1.0f);
+            if (kTrace) tr_drs = drs_now;
+            drs_f = drs_now ? drs_delta : 0.0f;
+            drs32 = drs_now ? drs32_on : 0.0f;
+            ahead_last = has_pred ? last_pred : 0.0f;  // (retired cars: 0, never read)
             t = __fadd_rn(t, -tl);  // (+inf stays +inf on lanes without a car)
         };
         auto emit_trace = [&](const int lap, const bool dnf_now) {
@@ -295,7 +327,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                         rec.position = dnf_now ? 0 : (uint8_t)(pl + 1);
                         rec.compound = (uint8_t)comp;
                         rec.tire_age = (uint8_t)(int)age;
-                        rec.flags = (uint8_t)((dnf_now ? 1 : 0) | (drs ? 2 : 0) | (tr_pit ? 4 : 0) | (tr_event << 4));
+                        rec.flags = (uint8_t)((dnf_now ? 1 : 0) | (tr_drs ? 2 : 0) | (tr_pit ? 4 : 0) | (tr_event << 4));
                         rec.gap = t;
                         out.trace[(((unsigned long long)race * out.trace_count + (s - out.trace_first)) * (unsigned)L + (unsigned)(lap - 1)) * (unsigned)n + lane] = rec;
                     }
@@ -305,64 +337,59 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             }
         };
 
-        full_rank(0.0f, dnf_lap <= 1);
+        full_rank(dnf_lap <= 1 ? kNaN : 0.0f);
         update_positions(1, dnf_lap <= 1);
         emit_trace(1, dnf_lap <= 1);
 
         // One lap >= 2.  z: this lap's pace noise; u12: overtake uniforms of passes 1 / 2 in the low / high half;
-        // u3: pass 3 (16 bits); ev: the words that decide the race events, looked at on lane `ev_lane` only.
-        auto run_lap = [&](const int lap, const float z, const uint32_t u12, const uint32_t u3, const uint4 ev, const int ev_lane) {
+        // u3: pass 3 (16 bits); ev: the word that decides the race event (compared on the event lane only: the
+        // thresholds are 0 on every other lane); roll: 16 bits for the VSC tyre roll-back.
+        auto run_lap = [&](const int lap, const float z, const uint32_t u12, const uint32_t u3, const uint32_t ev, const uint32_t roll) {
             const int rem = L - lap;
-            // ---- race-interrupting events (:168-176) ---------------------------------------------
-            {
-                const bool any_ev = lane == ev_lane && ((ev.x < red_thr) || (ev.y < sc_thr) || (ev.z < vsc_thr));
-                if (__any_sync(FULL, any_ev)) {  // rare (2.7 % of laps with the product probabilities)
-                    const int code = (ev.x < red_thr) ? 1 : (ev.y < sc_thr) ? 2 : ((ev.w < kVscRollThr) ? 4 : 3);
-                    const int e = __shfl_sync(FULL, code, ev_lane);
-                    const bool out_before = lap > dnf_lap;  // retired on an earlier lap (this lap's retirements still run here)
-                    const int pos_live = live_position(!out_before);
-                    if (kTrace) tr_event = e > 3 ? 3 : e;
-                    if (e == 1) {  // _handle_red_flag :397-431
-                        if (!out_before) {
-                            t = __fmul_rn(0.1f, (float)pos_live);
-                            age = 0.0f;
-                            comp = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
-                            used |= 1u << comp;
-                            tab.load(comp, eff, opt, pc);
-                        }
-                        drs_until = lap + 2;
-                    } else if (e == 2) {  // _handle_safety_car :334-376
-                        if (!out_before) {
-                            t = __fmul_rn(0.5f, (float)pos_live);
-                            age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
-                        }
-                        drs_until = lap + 2;
-                    } else {  // _handle_vsc :378-395
-                        if (!out_before) {
-                            t = __fmul_rn(t, 0.8f);
-                            if (e == 4) age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
-                        }
-                        drs_until = lap + 1;
+            // ---- race-interrupting events (:168-176): one draw on the cumulative thresholds ---------
+            if (__any_sync(FULL, ev < ev_any)) {  // rare (2.7 % of laps with the product probabilities)
+                const int code = ev < red_thr ? 1 : ev < sc_thr ? 2 : (roll < kVscRoll16 ? 4 : 3);
+                const int e = __shfl_sync(FULL, code, ev_lane);
+                const bool out_before = lap > dnf_lap;  // retired on an earlier lap (this lap's retirements still run here)
+                const int pos_live = live_position(!out_before);
+                if (kTrace) tr_event = e > 3 ? 3 : e;
+                if (e == 1) {  // _handle_red_flag :397-431
+                    if (!out_before) {
+                        t = __fmul_rn(0.1f, (float)pos_live);
+                        age = 0.0f;
+                        comp = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
+                        used |= 1u << comp;
+                        tab.load(comp, eff, opt, pc);
                     }
+                    drs_until = lap + 2;
+                } else if (e == 2) {  // _handle_safety_car :334-376
+                    if (!out_before) {
+                        t = __fmul_rn(0.5f, (float)pos_live);
+                        age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
+                    }
+                    drs_until = lap + 2;
+                } else {  // _handle_vsc :378-395
+                    if (!out_before) {
+                        t = __fmul_rn(t, 0.8f);
+                        if (e == 4) age = fmaxf(0.0f, __fadd_rn(age, -1.0f));
+                    }
+                    drs_until = lap + 1;
                 }
             }
 
             // ---- per-car lap (:186-223) --------------------------------------------------------
             const bool dnf = lap >= dnf_lap;
-            // _calculate_lap_time :313-332 (fuel is lap-uniform: every runner burns 1.5 kg per lap)
-            const float fuel_eff = __fmul_rn(fminf(110.0f, __fmul_rn(1.5f, (float)(lap - 1))), 0.03f);
-            const float fd = drs ? __fadd_rn(fuel_eff, drs_delta) : fuel_eff;
+            // _calculate_lap_time :313-332
+            fuel = fminf(3.3f, __fadd_rn(fuel, 0.045f));
             float x = __fmaf_rn(age, eff, pc);
-            x = __fadd_rn(x, -fd);
+            x = __fadd_rn(x, -fuel);
+            x = __fadd_rn(x, -drs_f);
             const float clean = __fmaf_rn(sigma, z, x);
-            float lt = clean;
-            if (t > 0.0f && ahead_last > 0.0f && t < dirty_thr)  // dirty air :208-216 (gap to the LEADER, Q3)
-                lt = fmaxf(__fadd_rn(clean, dirty_pen), ahead_last);
-            if (!dnf) {
-                t = __fadd_rn(t, lt);
-                last = lt;
-                age = __fadd_rn(age, 1.0f);
-            }
+            // dirty air :208-216 (gap to the LEADER, Q3); ahead_last is 0 for the leader and on lap 2
+            const float held = fmaxf(__fadd_rn(clean, dirty_pen), ahead_last);
+            last = (ahead_last > 0.0f && t < dirty_thr) ? held : clean;  // (a retired car's `last` is never read)
+            if (!dnf) t = __fadd_rn(t, last);
+            age = __fadd_rn(age, 1.0f);  // (retired cars age on: harmless, and one predicate less)
 
             // ---- _handle_pit_stops (:433-494) ----------------------------------------------
             const bool pit = !dnf && age > opt && rem > 5;
@@ -387,36 +414,29 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
             // overtake pace (x 2^15); NaN for a retired car blocks both pairs it sits in (Q5)
             const float op32 = dnf ? kNaN : __fmaf_rn(age, deg32, pace32);
-            const float opb = drs ? __fadd_rn(op32, -drs32_on) : op32;  // as the chasing car: DRS helps (:517-518)
+            const float opb = __fadd_rn(op32, -drs32);  // as the chasing car: DRS helps (:517-518)
             // First ordering of the lap.  `rank` still holds last lap's order; in 4 laps of 5 no car has moved more
             // than two places, so count crossings against the two old neighbours on each side only, then verify
             // (strictly sorted + a permutation) and fall back to the full count otherwise.
             {
-                if (is_car) W[rank] = t;
-                WARP_FENCE();
-                const float a1 = W[rank - 1], a2 = W[rank - 2], b1 = W[rank + 1], b2 = W[rank + 2];
+                if (is_car) sts_f<0>(wa, t);
+                const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
-                const int nr = rank + (int)moved;
-                const uint32_t nbit = 1u << (nr & 31);
-                WARP_FENCE();
-                if (is_car) REC[nr] = make_float4(t, op32, last, __int_as_float(lane));
-                const uint32_t cover = __reduce_or_sync(FULL, is_car ? nbit : 0u);
-                WARP_FENCE();
-                const float4 pv = REC[nr - 1];
-                const bool bad = is_car && !(pv.x < t);
+                set_rank(rank + (int)moved);
+                if (is_car) sts_f4<0>(ra, t, op32, last, 0.0f);
+                const uint32_t cover = __reduce_or_sync(FULL, is_car ? bit : 0u);
+                prev = lds_f4<-16>(ra);
+                const bool bad = is_car && !(prev.x < t);
                 have_rank = cover == nmask && !__any_sync(FULL, bad);
-                if (have_rank) { rank = nr; bit = nbit; prev = pv; }
-                WARP_FENCE();
             }
-#pragma unroll 1
-            for (int pass = 0; pass < 3; pass++) {
-                if (!have_rank) full_rank(op32, dnf);
+            // one pass; returns true when another pass may follow
+            auto one_pass = [&](const uint32_t u16) -> bool {
+                if (!have_rank) full_rank(op32);
                 const float delta = __fadd_rn(prev.y, -opb);  // pace_ahead - pace_behind (+ drs_delta), x 2^15
-                const uint32_t u16 = pass == 0 ? (u12 & 0xffffu) : pass == 1 ? (u12 >> 16) : u3;
                 // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling)
                 const bool succ = delta > ovt32 && (float)u16 < fminf(32768.0f, delta);
                 const uint32_t M = __reduce_or_sync(FULL, succ ? bit : 0u);
-                if (M == 0u) break;
+                if (M == 0u) return false;
                 // closed form of the sequential re-write chain :522-531 over runs of consecutive successes: with j the
                 // run start, k = rank - j and sn = "the car behind me succeeds too", the car ends on
                 // T[j] - 0.1 (k + sn) + 0.3 sn = T[j] - 0.1 (k - 2 sn); a car outside every run has k = sn = 0.
@@ -424,46 +444,44 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 const int j = 31 - __clz(clear_below);  // run start (bit 0 of M is never set)
                 const uint32_t above = ~((M >> rank) >> 1);  // bit i clear <=> pair (rank+i, rank+i+1) swapped
                 const int sn = (int)(~above & 1u);
-                const float base = REC[j].x;
+                const float base = lds_f<0>(rec_sh + 16u * (uint32_t)j);
                 if (is_car) t = __fmaf_rn(-0.1f, (float)(rank - j - 2 * sn), base);
                 // The new order is almost always the old one with every run [j, e] reversed (the re-written times
                 // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
                 // Verify the presumed order with one neighbour compare instead of re-counting all ranks.
-                const int r2 = j + (__ffs(above) - 1);  // j + e - rank with e = rank + ffs(above) - 1 the run end
-                WARP_FENCE();
-                if (is_car) REC[r2] = make_float4(t, op32, last, __int_as_float(lane));
-                WARP_FENCE();
-                const float4 pv = REC[r2 - 1];
-                const bool bad = is_car && !(pv.x < t);
+                set_rank(j + (__ffs(above) - 1));  // j + e - rank with e = rank + ffs(above) - 1 the run end
+                if (is_car) sts_f4<0>(ra, t, op32, last, 0.0f);
+                prev = lds_f4<-16>(ra);
+                const bool bad = is_car && !(prev.x < t);
                 have_rank = !__any_sync(FULL, bad);
-                if (have_rank) { rank = r2; bit = 1u << (r2 & 31); prev = pv; }
-                WARP_FENCE();
-            }
-            if (!have_rank) full_rank(op32, dnf);
+                return true;
+            };
+            if (one_pass(u12 & 0xffffu))
+                if (one_pass(u12 >> 16)) one_pass(u3);
+            if (!have_rank) full_rank(op32);
             update_positions(lap, dnf);
             emit_trace(lap, dnf);
         };
 
         for (int lap = 2; lap <= L; lap += 2) {
             // one Philox call per lane per lap PAIR: x, y -> Box-Muller pair (cos: this lap, sin: the next);
-            // z -> this lap's overtake passes 1, 2; w -> the next lap's; passes 3 come from a borrowed word
+            // z -> this lap's overtake passes 1, 2; w -> the next lap's; passes 3 come from a borrowed word.
+            // Event lane (31, or the virtual lane 64 when there are more than 20 cars): x, y -> the event draws of
+            // the two laps, z -> the two 16-bit VSC roll-back draws.
             const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, key);
             uint32_t extra;
-            uint4 ev0, ev1;
-            if (kSmall) {  // lanes 20..29 lend x (to drivers 0..9) and y (to drivers 10..19); lanes 31 / 30 decide the events
+            uint4 ev = w;
+            if (kSmall) {  // lanes 20..29 lend x (to drivers 0..9) and y (to drivers 10..19)
                 const uint32_t e1 = __shfl_sync(FULL, w.x, lend_lane), e2 = __shfl_sync(FULL, w.y, lend_lane);
                 extra = lane < 10 ? e1 : e2;
-                ev0 = w;
-                ev1 = w;
-            } else {  // up to 32 cars: a second call per lane, and two warp-uniform calls for the events
+            } else {  // up to 32 cars: a second call per lane, and one warp-uniform call for the events
                 extra = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)(lane + 32), stream, key).x;
-                ev0 = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 64u, stream, key);
-                ev1 = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 65u, stream, key);
+                ev = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 64u, stream, key);
             }
             float za, zb;
             if (kExact) exact_normal2(w.x, w.y, za, zb); else fast_normal2(w.x, w.y, za, zb);
-            run_lap(lap, za, w.z, extra & 0xffffu, ev0, 31);
-            if (lap + 1 <= L) run_lap(lap + 1, zb, w.w, extra >> 16, ev1, 30);
+            run_lap(lap, za, w.z, extra & 0xffffu, ev.x, ev.z & 0xffffu);
+            if (lap + 1 <= L) run_lap(lap + 1, zb, w.w, extra >> 16, ev.y, ev.z >> 16);
         }
         const bool dnf = L >= dnf_lap;
         const int pos_live = live_position(!dnf);

@@ -12,8 +12,8 @@
  *              sin: lap l+1); word2 lo/hi 16 -> lap l overtake pass 1/2; word3 -> the same for lap l+1;
  *              pass 3 of laps l / l+1 = lo / hi 16 bits of a borrowed word: n <= 20: word0 of lane 20+d (d < 10)
  *              or word1 of lane 10+d (d >= 10); n > 20: word0 of lane 32+d.
- *              events (red / SC / VSC / VSC tyre roll-back = words 0..3): n <= 20: lane 31 for lap l, lane 30
- *              for lap l+1; n > 20: lanes 64 / 65
+ *              events: red, else SC, else VSC decided by ONE word against cumulative thresholds -- word0 (lap l) /
+ *              word1 (lap l+1) of lane 31 (n <= 20) or lane 64 (n > 20); VSC tyre roll-back: lo / hi 16 bits of word2
  *   - FP32, every fused op explicit (fmaf), times re-based on the leader after every lap,
  *     overtake chains in closed form  base - 0.1*(k - 2*sn), ordering by (time, driver index).
  * With the "exact" normal generator (IEEE-only arithmetic) kernel and mirror agree bit for bit; the
@@ -102,6 +102,7 @@ static uint32_t prob_threshold(double p) {
     return (uint32_t)floor(p * 4294967296.0);
 }
 
+static double clamp01(double p) { return !(p > 0.0) ? 0.0 : p > 1.0 ? 1.0 : p; }
 #define DNF_NEVER (-1e30f)
 static float dnf_scale(double rate) { /* 1 / ln(1 - rate) on the 2^-32 probability grid */
     const double thr = (double)prob_threshold(rate) / 4294967296.0;
@@ -126,7 +127,14 @@ static void derive(const orc_params* p, nat_t* o) {
     o->n = n; o->L = p->total_laps; o->track = p->track_condition;
     o->pit_loss = (float)p->pit_loss; o->ovt_delta = (float)p->overtake_delta; o->drs_delta = (float)p->drs_delta;
     o->dirty_thr = (float)p->dirty_thr; o->dirty_pen = (float)p->dirty_pen;
-    o->red_thr = prob_threshold(p->red_p); o->sc_thr = prob_threshold(p->sc_p); o->vsc_thr = prob_threshold(p->vsc_p);
+    { /* red flag, else SC, else VSC: one draw against the cumulative probabilities */
+        const double pr = clamp01(p->red_p), ps = clamp01(p->sc_p), pv = clamp01(p->vsc_p);
+        o->red_thr = prob_threshold(pr);
+        o->sc_thr = prob_threshold(pr + (1.0 - pr) * ps);
+        o->vsc_thr = prob_threshold(pr + (1.0 - pr) * (ps + (1.0 - ps) * pv));
+        if (o->sc_thr < o->red_thr) o->sc_thr = o->red_thr;
+        if (o->vsc_thr < o->sc_thr) o->vsc_thr = o->sc_thr;
+    }
     for (int d = 0; d < n; d++) {
         o->pace[d] = (float)p->base_pace[d]; o->deg_ovt[d] = (float)p->tire_deg[d]; o->sigma[d] = (float)p->variance[d];
         o->dnf_scale[d] = dnf_scale(p->dnf_rate[d]);
@@ -186,7 +194,7 @@ static void update_positions(ncar* cars, int n, int lap, int drs_until) {
     const int drs_on = lap > 2 && lap > drs_until;
     for (int r = 0; r < n; r++) {
         ncar* c = &cars[ord[r]];
-        if (c->dnf) continue;
+        if (c->dnf) { c->drs = 0; continue; }
         if (!have) { tl = c->t; have = 1; }
         c->pos_live = i++;
         c->drs = pred >= 0 && drs_on && (c->t + -cars[pred].t < 1.0f);
@@ -289,13 +297,15 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
         memset(pitted, 0, sizeof(pitted));
         emit_trace(trace, s, L, n, 1, cars, pitted, 0);
 
+        float fuel = 0.0f;
         float zn[N32];   /* the second Box-Muller variate, kept for the odd lap of the pair */
         uint32_t u12[N32], u3[N32];
         for (int lap = 2; lap <= L; lap++) {
             const uint32_t pair = (uint32_t)(lap & ~1), odd = (uint32_t)(lap & 1);
             /* ---- events :168-176 ---- */
-            u4 we = philox(s0, s1, (pair << 8) | (n <= 20 ? 31u - odd : 64u + odd), stream, k0, k1);
-            const int ev = we.x < R.red_thr ? 1 : we.y < R.sc_thr ? 2 : we.z < R.vsc_thr ? (we.w < 1288490188u ? 4 : 3) : 0;
+            const u4 we = philox(s0, s1, (pair << 8) | (n <= 20 ? 31u : 64u), stream, k0, k1);
+            const uint32_t evw = odd ? we.y : we.x, roll = odd ? we.z >> 16 : we.z & 0xffffu;
+            const int ev = evw < R.red_thr ? 1 : evw < R.sc_thr ? 2 : evw < R.vsc_thr ? (roll < 19660u ? 4 : 3) : 0;
             const int rem = L - lap;
             const int nc_rule = R.track == 2 ? 4 : R.track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
             if (ev) {
@@ -315,7 +325,7 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
                 drs_until = ev >= 3 ? lap + 1 : lap + 2;
             }
             /* ---- per-car lap :186-223 ---- */
-            const float fuel_eff = fminf(110.0f, 1.5f * (float)(lap - 1)) * 0.03f;
+            fuel = fminf(3.3f, fuel + 0.045f); /* (110 - fuel_load) * 0.03, every runner burns 1.5 kg per lap */
             for (int d = 0; d < n; d++) {
                 ncar* c = &cars[d];
                 const uint32_t extra = n <= 20 ? (d < 10 ? philox(s0, s1, (pair << 8) | (uint32_t)(20 + d), stream, k0, k1).x
@@ -332,14 +342,15 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
                     u12[d] = w[d].w;
                     u3[d] = extra >> 16;
                 }
-                if (c->dnf) continue;
-                if (lap >= c->dnf_lap) { c->dnf = 1; continue; }
-                const float fd = c->drs ? fuel_eff + R.drs_delta : fuel_eff;
+                if (lap >= c->dnf_lap) c->dnf = 1;
+                if (c->dnf) { c->age = c->age + 1.0f; continue; } /* (the kernel lets retired cars age on; never used) */
                 float x = fmaf(c->age, c->eff, c->pc);
-                x = x + -fd;
+                x = x + -fuel;
+                x = x + -(c->drs ? R.drs_delta : 0.0f);
                 const float clean = fmaf(R.sigma[d], z, x);
                 float lt = clean;
-                if (c->t > 0.0f && c->ahead_last > 0.0f && c->t < R.dirty_thr) lt = fmaxf(clean + R.dirty_pen, c->ahead_last);
+                /* ahead_last is 0 for the leader: the reference's `time_behind_leader > 0` is implied */
+                if (c->ahead_last > 0.0f && c->t < R.dirty_thr) lt = fmaxf(clean + R.dirty_pen, c->ahead_last);
                 c->t = c->t + lt;
                 c->last = lt;
                 c->age = c->age + 1.0f;
