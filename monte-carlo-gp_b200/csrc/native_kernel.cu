@@ -102,6 +102,7 @@ __device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int 
     // exact ties are measure-zero events; detect them by a hole in the rank set and fix up
     const uint32_t seen = __reduce_or_sync(FULL, lane < n ? (1u << cnt) : 0u);
     if (seen != nmask) {
+#pragma unroll 1
         for (int j = 0; j < lane; j++) cnt += (S_t[j] == t) ? 1 : 0;
     }
     WARP_FENCE();
@@ -429,14 +430,18 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 const bool bad = is_car && !(prev.x < t);
                 have_rank = cover == nmask && !__any_sync(FULL, bad);
             }
-            // one pass; returns true when another pass may follow
-            auto one_pass = [&](const uint32_t u16) -> bool {
+            // Up to three passes.  The loop head is the ONE place where a lost order is re-established by counting
+            // (after a failed window placement, after a failed run reversal, and before leaving).
+            uint32_t uw = u12;  // low half: this pass's 16-bit uniform
+#pragma unroll 1
+            for (int pass = 0;; pass++) {
                 if (!have_rank) full_rank(op32);
+                if (pass == 3) break;
                 const float delta = __fadd_rn(prev.y, -opb);  // pace_ahead - pace_behind (+ drs_delta), x 2^15
                 // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling)
-                const bool succ = delta > ovt32 && (float)u16 < fminf(32768.0f, delta);
+                const bool succ = delta > ovt32 && (float)(uw & 0xffffu) < fminf(32768.0f, delta);
                 const uint32_t M = __reduce_or_sync(FULL, succ ? bit : 0u);
-                if (M == 0u) return false;
+                if (M == 0u) break;
                 // closed form of the sequential re-write chain :522-531 over runs of consecutive successes: with j the
                 // run start, k = rank - j and sn = "the car behind me succeeds too", the car ends on
                 // T[j] - 0.1 (k + sn) + 0.3 sn = T[j] - 0.1 (k - 2 sn); a car outside every run has k = sn = 0.
@@ -454,34 +459,42 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 prev = lds_f4<-16>(ra);
                 const bool bad = is_car && !(prev.x < t);
                 have_rank = !__any_sync(FULL, bad);
-                return true;
-            };
-            if (one_pass(u12 & 0xffffu))
-                if (one_pass(u12 >> 16)) one_pass(u3);
-            if (!have_rank) full_rank(op32);
+                uw = __funnelshift_r(uw, u3, 16);  // pass 2: high half of u12; pass 3: u3
+            }
             update_positions(lap, dnf);
             emit_trace(lap, dnf);
         };
 
-        for (int lap = 2; lap <= L; lap += 2) {
-            // one Philox call per lane per lap PAIR: x, y -> Box-Muller pair (cos: this lap, sin: the next);
-            // z -> this lap's overtake passes 1, 2; w -> the next lap's; passes 3 come from a borrowed word.
-            // Event lane (31, or the virtual lane 64 when there are more than 20 cars): x, y -> the event draws of
-            // the two laps, z -> the two 16-bit VSC roll-back draws.
-            const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, key);
-            uint32_t extra;
-            uint4 ev = w;
-            if (kSmall) {  // lanes 20..29 lend x (to drivers 0..9) and y (to drivers 10..19)
-                const uint32_t e1 = __shfl_sync(FULL, w.x, lend_lane), e2 = __shfl_sync(FULL, w.y, lend_lane);
-                extra = lane < 10 ? e1 : e2;
-            } else {  // up to 32 cars: a second call per lane, and one warp-uniform call for the events
-                extra = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)(lane + 32), stream, key).x;
-                ev = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 64u, stream, key);
+        // One Philox call per lane per lap PAIR (made on the even lap): x, y -> Box-Muller pair (cos: this lap, sin:
+        // the next); z -> this lap's overtake passes 1, 2; w -> the next lap's; passes 3 come from a borrowed word.
+        // Event lane (31, or the virtual lane 64 when there are more than 20 cars): x, y -> the event draws of the
+        // two laps, z -> the two 16-bit VSC roll-back draws.
+        float z_nx = 0.0f;
+        uint32_t u12_nx = 0u, u3_nx = 0u, ev_nx = 0u, roll_nx = 0u;
+#pragma unroll 1
+        for (int lap = 2; lap <= L; lap++) {
+            float z;
+            uint32_t u12, u3, evw, roll;
+            if ((lap & 1) == 0) {
+                const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, key);
+                uint32_t extra;
+                uint4 ev = w;
+                if (kSmall) {  // lanes 20..29 lend x (to drivers 0..9) and y (to drivers 10..19)
+                    const uint32_t e1 = __shfl_sync(FULL, w.x, lend_lane), e2 = __shfl_sync(FULL, w.y, lend_lane);
+                    extra = lane < 10 ? e1 : e2;
+                } else {  // up to 32 cars: a second call per lane, and one warp-uniform call for the events
+                    extra = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)(lane + 32), stream, key).x;
+                    ev = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 64u, stream, key);
+                }
+                if (kExact) exact_normal2(w.x, w.y, z, z_nx); else fast_normal2(w.x, w.y, z, z_nx);
+                u12 = w.z; u12_nx = w.w;
+                u3 = extra & 0xffffu; u3_nx = extra >> 16;
+                evw = ev.x; ev_nx = ev.y;
+                roll = ev.z & 0xffffu; roll_nx = ev.z >> 16;
+            } else {
+                z = z_nx; u12 = u12_nx; u3 = u3_nx; evw = ev_nx; roll = roll_nx;
             }
-            float za, zb;
-            if (kExact) exact_normal2(w.x, w.y, za, zb); else fast_normal2(w.x, w.y, za, zb);
-            run_lap(lap, za, w.z, extra & 0xffffu, ev.x, ev.z & 0xffffu);
-            if (lap + 1 <= L) run_lap(lap + 1, zb, w.w, extra >> 16, ev.y, ev.z >> 16);
+            run_lap(lap, z, u12, u3, evw, roll);
         }
         const bool dnf = L >= dnf_lap;
         const int pos_live = live_position(!dnf);
