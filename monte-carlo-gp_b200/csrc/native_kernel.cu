@@ -263,7 +263,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         int drs_until = 0;
         int rank;
         uint32_t bit;          // 1 << rank
-        uint32_t wa, ra;       // shared addresses of W[rank] and REC[rank]
+        uint32_t ra;           // shared address of REC[rank]
         float4 prev;           // record of the car one rank ahead (REC[rank - 1]), valid whenever have_rank
         bool have_rank;        // warp-uniform: rank / bit / wa / ra / prev / REC describe the current times
         float drs_f = 0.0f, drs32 = 0.0f;  // drs_delta (and x 2^15) while DRS is enabled for this car, else 0
@@ -275,7 +275,6 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         auto set_rank = [&](int r) {
             rank = r;
             bit = 1u << (r & 31);
-            wa = w_sh + 4u * (uint32_t)r;
             ra = rec_sh + 16u * (uint32_t)r;
         };
         // all-cars rank by counting, then publish the records
@@ -420,6 +419,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             // than two places, so count crossings against the two old neighbours on each side only, then verify
             // (strictly sorted + a permutation) and fall back to the full count otherwise.
             {
+                const uint32_t wa = w_sh + 4u * (uint32_t)rank;
                 if (is_car) sts_f<0>(wa, t);
                 const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
@@ -430,18 +430,14 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 const bool bad = is_car && !(prev.x < t);
                 have_rank = cover == nmask && !__any_sync(FULL, bad);
             }
-            // Up to three passes.  The loop head is the ONE place where a lost order is re-established by counting
-            // (after a failed window placement, after a failed run reversal, and before leaving).
-            uint32_t uw = u12;  // low half: this pass's 16-bit uniform
-#pragma unroll 1
-            for (int pass = 0;; pass++) {
+            // one pass; returns true when another pass may follow
+            auto one_pass = [&](const uint32_t u16) -> bool {
                 if (!have_rank) full_rank(op32);
-                if (pass == 3) break;
                 const float delta = __fadd_rn(prev.y, -opb);  // pace_ahead - pace_behind (+ drs_delta), x 2^15
                 // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling)
-                const bool succ = delta > ovt32 && (float)(uw & 0xffffu) < fminf(32768.0f, delta);
+                const bool succ = delta > ovt32 && (float)u16 < fminf(32768.0f, delta);
                 const uint32_t M = __reduce_or_sync(FULL, succ ? bit : 0u);
-                if (M == 0u) break;
+                if (M == 0u) return false;
                 // closed form of the sequential re-write chain :522-531 over runs of consecutive successes: with j the
                 // run start, k = rank - j and sn = "the car behind me succeeds too", the car ends on
                 // T[j] - 0.1 (k + sn) + 0.3 sn = T[j] - 0.1 (k - 2 sn); a car outside every run has k = sn = 0.
@@ -459,8 +455,11 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 prev = lds_f4<-16>(ra);
                 const bool bad = is_car && !(prev.x < t);
                 have_rank = !__any_sync(FULL, bad);
-                uw = __funnelshift_r(uw, u3, 16);  // pass 2: high half of u12; pass 3: u3
-            }
+                return true;
+            };
+            if (one_pass(u12 & 0xffffu))
+                if (one_pass(u12 >> 16)) one_pass(u3);
+            if (!have_rank) full_rank(op32);
             update_positions(lap, dnf);
             emit_trace(lap, dnf);
         };
