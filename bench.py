@@ -33,6 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W_RACE = {57: 17100, 78: 23190}  # algorithmic warp-instructions per race, SURVEY.md §8(d)
+# From the committed ncu capture of this kernel build (profiles/, `ncu --set full`, 2 M races, one launch):
+NCU = {"capture": "profiles/r1g_native_kernel_ncu_raw.csv", "executed_warp_instr_per_race": 12506.0,
+       "dram_bytes_per_launch": 41728}
 N_DRIVERS, LAPS = 20, 57
 WORKLOAD = "bahrain57: 20 drivers x 57 laps, native Philox4x32-10/FP32, synthetic inputs of SURVEY 8(d)"
 
@@ -292,7 +295,7 @@ def main():
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_cpu = args.cpu_sims or 50000 * cores
+        n_cpu = args.cpu_sims or 120000 * cores   # ~12 s of CPU work
         dt, n_done = cpu_run(n_cpu, 42, cores)
         cpu = {"value": n_done / dt, "unit": "races/s", "cores": cores, "kind": "port",
                "sample": f"{n_done} sims of the same race, {cores} threads, {dt:.1f} s; C restatement of src/simulation.py "
@@ -323,9 +326,13 @@ def main():
             "roofline": {"bound": "alu_issue", "achieved": achieved, "peak": peak, "unit": "Twarp-instr/s per GPU",
                          "frac": achieved / peak, "frac_at_sampled_clock": achieved / peak_run,
                          "algorithmic_warp_instr_per_race": w_race(LAPS), "sm_count": sm_count, "f_sm_mhz_max": f_max,
-                         "f_sm_mhz_sampled": f_run, "traffic": None,
+                         "f_sm_mhz_sampled": f_run, "traffic": NCU["dram_bytes_per_launch"],
+                         "executed_warp_instr_per_race": NCU["executed_warp_instr_per_race"],
+                         "issue_slot_utilisation": per_gpu * NCU["executed_warp_instr_per_race"] / 1e12 / peak,
                          "note": "no dense contraction and ~0 HBM traffic (SURVEY 8(d)): the bound is warp-instruction issue, "
-                                 "N_SM x 4 x f_SM; executed-instruction counts from ncu are in profiles/"},
+                                 "N_SM x 4 x f_SM.  frac = ALGORITHMIC work (17 100 warp-instr per race, SURVEY 8(d)) / peak; "
+                                 "issue_slot_utilisation = instructions this kernel actually executes (ncu, "
+                                 + NCU["capture"] + ") x races/s / peak; traffic = dram bytes read+written per launch (ncu)"},
             "cpu_baseline": cpu,
             "replay_mode": replay,
         }

@@ -505,13 +505,12 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             // retired cars: later lap first, then larger time, then grid order (stable sort, reverse=True)
             const float tc = dnf_lap == 1 ? 0.0f : t;
             int worse = 0;
-            for (int j = 0; j < n; j++) {
+            for (uint32_t dm = __ballot_sync(FULL, is_car && dnf); dm; dm &= dm - 1u) {  // retired cars only (~1 per race)
+                const int j = __ffs(dm) - 1;
                 const int jl = __shfl_sync(FULL, dnf_lap, j);
                 const float jt = __shfl_sync(FULL, tc, j);
                 const int js = __shfl_sync(FULL, slot, j);
-                const bool jd = jl <= L;
-                const bool ahead = jd && j != lane &&
-                                   (jl > dnf_lap || (jl == dnf_lap && (jt > tc || (jt == tc && js < slot))));
+                const bool ahead = j != lane && (jl > dnf_lap || (jl == dnf_lap && (jt > tc || (jt == tc && js < slot))));
                 worse += ahead ? 1 : 0;
             }
             const int pos = live ? pos_live : n_live + worse;
