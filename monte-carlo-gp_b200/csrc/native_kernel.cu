@@ -80,12 +80,14 @@ __device__ __forceinline__ float lt_one(float a, float b) {
     return m;
 }
 
-// Rank of this lane's time among the n cars (ascending, ties broken by lane).  S_t: 32 floats of warp scratch;
-// every lane reads all keys back with broadcast LDS.128s and counts with FSET.BF + FADD (2 instr per key, one on
-// each math pipe, four independent accumulation chains).
+// Rank of this lane's time among all 32 lanes (ascending, ties broken by lane).  S_t: 32 floats of warp scratch;
+// every lane reads the keys back with broadcast LDS.128s and counts with FSET.BF + FADD (2 instr per key, one on
+// each math pipe, four independent accumulation chains).  Lanes without a car hold huge, increasing "parked" times,
+// so they rank behind every car in lane order; with NV4 == 5 only the first 20 keys are read and `park` (lane - 20
+// on lanes >= 20, else 0) completes their count.
 template <int NV4>
-__device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int n, uint32_t nmask) {
-    S_t[lane] = t;  // lanes >= n pass +inf
+__device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int park) {
+    S_t[lane] = t;
     WARP_FENCE();
     const float4* v4 = reinterpret_cast<const float4*>(S_t);
     const float4 v0 = v4[0];
@@ -98,10 +100,10 @@ __device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int 
         c2 += lt_one(v.z, t);
         c3 += lt_one(v.w, t);
     }
-    int cnt = (int)((c0 + c1) + (c2 + c3));
+    int cnt = (int)((c0 + c1) + (c2 + c3)) + park;
     // exact ties are measure-zero events; detect them by a hole in the rank set and fix up
-    const uint32_t seen = __reduce_or_sync(FULL, lane < n ? (1u << cnt) : 0u);
-    if (seen != nmask) {
+    const uint32_t seen = __reduce_or_sync(FULL, 1u << (cnt & 31));
+    if (seen != FULL) {
 #pragma unroll 1
         for (int j = 0; j < lane; j++) cnt += (S_t[j] == t) ? 1 : 0;
     }
@@ -157,7 +159,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     const int lane = threadIdx.x & 31, warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
     const float kInf = __int_as_float(0x7f800000), kNaN = __int_as_float(0x7fc00000);
     float* S_t = S_t_all[warp];
-    float* W = S_w_all[warp] + 8;   // W[-8..-1] = -inf, W[0..n) = times by rank, W[n..40) = +inf: no index guards needed
+    float* W = S_w_all[warp] + 8;   // W[-8..-1] = -inf, W[0..32) = times by rank, W[32..40) = +inf: no index guards needed
     float4* REC = S_rec_all[warp] + 2;  // REC[-1] = {-inf, NaN, 0, -}: "no car ahead" blocks the pair and ends the order check
     W[lane - 8] = lane < 8 ? -kInf : kInf;
     if (lane < 16) W[lane + 24] = kInf;
@@ -166,8 +168,11 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     const uint32_t w_sh = smem_u32(W), rec_sh = smem_u32(REC);
     const int n = __shfl_sync(FULL, R.n, 0), L = __shfl_sync(FULL, R.total_laps, 0), track = __shfl_sync(FULL, R.track, 0);
     const bool grid_fixed = __shfl_sync(FULL, R.grid_fixed, 0) != 0;
-    const uint32_t nmask = n >= 32 ? FULL : ((1u << n) - 1u);
     const bool is_car = lane < n;
+    // Lanes without a car behave like cars parked behind the field for good: a huge time that grows with the lane,
+    // retired from lap 0 (NaN overtake pace).  No per-lap code then needs an `is_car` guard.
+    const float park_t = __fmul_rn(1e30f, (float)(lane + 1));
+    const int park = (NV4 == 5 && lane >= 20) ? lane - 20 : 0;
     // overtake paces are carried pre-scaled by 2^15 (exact) so that the 16-bit uniform compares against them directly
     const float pace32 = __fmul_rn(R.pace[lane], 32768.0f), deg32 = __fmul_rn(R.deg_ovt[lane], 32768.0f), sigma = R.sigma[lane];
     const float dnf_scale = R.dnf_scale[lane];
@@ -256,7 +261,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             if (slot < 3) sd = fminf(sd, 1.0f);
             const float lt = __fmaf_rn(-0.5f, sd, x);
             // retired on lap 1: distinct sentinel times below every runner; lanes without a car: +inf for good
-            t = !is_car ? kInf : dnf_lap == 1 ? -(float)(lane + 1) : lt;
+            t = !is_car ? park_t : dnf_lap == 1 ? -(float)(lane + 1) : lt;
             age = __fadd_rn(age, 1.0f);
         }
 
@@ -279,8 +284,8 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         };
         // all-cars rank by counting, then publish the records
         auto full_rank = [&](float op32) {
-            set_rank(rank_by_count<NV4>(t, S_t, lane, n, nmask));
-            if (is_car) sts_f4<0>(ra, t, op32, last, 0.0f);
+            set_rank(rank_by_count<NV4>(t, S_t, lane, park));
+            sts_f4<0>(ra, t, op32, last, 0.0f);
             prev = lds_f4<-16>(ra);
             have_rank = true;
         };
@@ -420,15 +425,14 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             // (strictly sorted + a permutation) and fall back to the full count otherwise.
             {
                 const uint32_t wa = w_sh + 4u * (uint32_t)rank;
-                if (is_car) sts_f<0>(wa, t);
+                sts_f<0>(wa, t);
                 const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
                 set_rank(rank + (int)moved);
-                if (is_car) sts_f4<0>(ra, t, op32, last, 0.0f);
-                const uint32_t cover = __reduce_or_sync(FULL, is_car ? bit : 0u);
+                sts_f4<0>(ra, t, op32, last, 0.0f);
+                const uint32_t cover = __reduce_or_sync(FULL, bit);
                 prev = lds_f4<-16>(ra);
-                const bool bad = is_car && !(prev.x < t);
-                have_rank = cover == nmask && !__any_sync(FULL, bad);
+                have_rank = cover == FULL && !__any_sync(FULL, !(prev.x < t));
             }
             // one pass; returns true when another pass may follow
             auto one_pass = [&](const uint32_t u16) -> bool {
@@ -446,15 +450,14 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 const uint32_t above = ~((M >> rank) >> 1);  // bit i clear <=> pair (rank+i, rank+i+1) swapped
                 const int sn = (int)(~above & 1u);
                 const float base = lds_f<0>(rec_sh + 16u * (uint32_t)j);
-                if (is_car) t = __fmaf_rn(-0.1f, (float)(rank - j - 2 * sn), base);
+                t = __fmaf_rn(-0.1f, (float)(rank - j - 2 * sn), base);  // (k = sn = 0: base is the car's own time)
                 // The new order is almost always the old one with every run [j, e] reversed (the re-written times
                 // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
                 // Verify the presumed order with one neighbour compare instead of re-counting all ranks.
                 set_rank(j + (__ffs(above) - 1));  // j + e - rank with e = rank + ffs(above) - 1 the run end
-                if (is_car) sts_f4<0>(ra, t, op32, last, 0.0f);
+                sts_f4<0>(ra, t, op32, last, 0.0f);
                 prev = lds_f4<-16>(ra);
-                const bool bad = is_car && !(prev.x < t);
-                have_rank = !__any_sync(FULL, bad);
+                have_rank = !__any_sync(FULL, !(prev.x < t));
                 return true;
             };
             if (one_pass(u12 & 0xffffu))
