@@ -218,7 +218,7 @@ def main():
         ev[k][0].record()
         step(args.warmup + k)
         ev[k][1].record()
-        launches += 1
+        launches += sharded.engine.last_launch_count     # the library's own count for this step (counter reset + race kernel)
     barrier()
     t_wall1 = time.perf_counter()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)

@@ -15,7 +15,8 @@ namespace mcgp {
 cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, unsigned long long n_sims,
                           unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
-                          unsigned long long trace_first, unsigned long long trace_count, int sm_count, cudaStream_t st);
+                          unsigned long long trace_first, unsigned long long trace_count, unsigned long long* work_counter,
+                          int sm_count, cudaStream_t st);
 cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status, int sm_count,
@@ -29,6 +30,7 @@ struct mcgp_context {
     std::string err;
     NativeRace* native_dev = nullptr;
     ReplayRace* replay_dev = nullptr;
+    unsigned long long* work_counter = nullptr;  // one claim counter per race of the batch (dynamic sim distribution)
     int n_races = 0, n_drivers = 0;
     int launches = 0;
     // grow-only scratch for the host-buffer entry points
@@ -209,6 +211,7 @@ int mcgp_destroy(mcgp_handle h) {
     cudaSetDevice(h->device);
     if (h->native_dev) cudaFree(h->native_dev);
     if (h->replay_dev) cudaFree(h->replay_dev);
+    if (h->work_counter) cudaFree(h->work_counter);
     for (int i = 0; i < 8; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
     delete h;
     return MCGP_OK;
@@ -244,7 +247,9 @@ int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races)
     for (int r = 0; r < n_races; r++) { derive_native(&races[r], &nat[r]); derive_replay(&races[r], &rep[r]); }
     if (h->native_dev) { cudaFree(h->native_dev); h->native_dev = nullptr; }
     if (h->replay_dev) { cudaFree(h->replay_dev); h->replay_dev = nullptr; }
+    if (h->work_counter) { cudaFree(h->work_counter); h->work_counter = nullptr; }
     cudaError_t e = cudaMalloc(&h->native_dev, sizeof(NativeRace) * n_races);
+    if (e == cudaSuccess) e = cudaMalloc(&h->work_counter, sizeof(unsigned long long) * n_races);
     if (e == cudaSuccess) e = cudaMalloc(&h->replay_dev, sizeof(ReplayRace) * n_races);
     if (e == cudaSuccess) e = cudaMemcpy(h->native_dev, nat, sizeof(NativeRace) * n_races, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->replay_dev, rep, sizeof(ReplayRace) * n_races, cudaMemcpyHostToDevice);
@@ -268,8 +273,8 @@ static int launch_native_common(mcgp_handle h, uint64_t n_sims, uint64_t sim_beg
     static_assert(sizeof(mcgp_trace_record) == sizeof(TraceRecord) && sizeof(TraceRecord) == 8, "trace record layout");
     CU(mcgp::launch_native(h->native_dev, h->n_races, h->n_drivers, n_sims, sim_begin, seed, (flags & MCGP_F_EXACT_NORMAL) != 0,
                            (unsigned long long*)hist_dev, finish_dev, times_dev, (TraceRecord*)(trace_count ? trace_dev : nullptr),
-                           trace_first, trace_count, h->sm_count, (cudaStream_t)cuda_stream));
-    h->launches = 1;
+                           trace_first, trace_count, h->work_counter, h->sm_count, (cudaStream_t)cuda_stream));
+    h->launches = 2;  // the claim-counter reset + the race kernel
     return MCGP_OK;
 }
 

@@ -134,7 +134,7 @@ template <int NV4, bool kExact, int kOut>
 __global__ void __launch_bounds__(kThreads, MCGP_MIN_BLOCKS)
 native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_sims, unsigned long long sim_begin,
                    const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
-                   const __grid_constant__ NativeOutputs out) {
+                   const __grid_constant__ NativeOutputs out, unsigned long long* __restrict__ work_counter) {
     constexpr bool kDetail = kOut >= 1, kTrace = kOut >= 2;
     constexpr bool kSmall = NV4 == 5;  // n <= 20: lanes 20..31 carry no car and lend their Philox words
     uint8_t* __restrict__ finish = out.finish;
@@ -188,8 +188,14 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     const int lend_lane = 20 + (lane < 10 ? lane : lane < 20 ? lane - 10 : 0);  // kSmall: whose spare words this lane borrows
     const Tables tab{&R, lane};
 
-    const unsigned long long warps_per_race = (unsigned long long)gridDim.x * kWarpsPerBlock;
-    for (unsigned long long s = (unsigned long long)blockIdx.x * kWarpsPerBlock + (unsigned)warp; s < n_sims; s += warps_per_race) {
+    // Sims are handed out dynamically: a warp's first sim is its global warp index, every further one is claimed from
+    // the race's counter (host-initialised to the number of warps) -- one atomic per race, issued a whole race ahead
+    // of its use.  The warp scheduler favours some warps over others, so an even static split left 20 % of the
+    // warp-slots idle at the end; which warp runs which sim does not matter (draws are keyed by the sim index).
+    unsigned long long* const claim = work_counter + race;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * kWarpsPerBlock + (unsigned)warp; s < n_sims;) {
+        unsigned long long s_next = 0;
+        if (lane == 0) s_next = atomicAdd(claim, 1ull);
         const unsigned long long sim = sim_begin + s;
         const uint32_t sim_lo = (uint32_t)sim, sim_hi = (uint32_t)(sim >> 32);
 
@@ -526,6 +532,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 }
             }
         }
+        s = __shfl_sync(FULL, s_next, 0);
     }
 
     __syncthreads();
@@ -535,19 +542,26 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     }
 }
 
+// every race's claim counter starts behind the statically assigned first sims
+__global__ void init_work_counters(unsigned long long* wc, int n_races, unsigned long long first) {
+    for (int i = threadIdx.x; i < n_races; i += blockDim.x) wc[i] = first;
+}
+
 // ---- host-side launcher ------------------------------------------------------------------------
 template <int NV4, bool kExact>
 static void launch_out(int kout, dim3 grid, dim3 block, cudaStream_t st, const NativeRace* races_dev, unsigned long long n_sims,
-                       unsigned long long sim_begin, const PhiloxKeys& key, unsigned long long* hist, const NativeOutputs& out) {
-    if (kout == 0) native_race_kernel<NV4, kExact, 0><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out);
-    else if (kout == 1) native_race_kernel<NV4, kExact, 1><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out);
-    else native_race_kernel<NV4, kExact, 2><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out);
+                       unsigned long long sim_begin, const PhiloxKeys& key, unsigned long long* hist, const NativeOutputs& out,
+                       unsigned long long* wc) {
+    if (kout == 0) native_race_kernel<NV4, kExact, 0><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out, wc);
+    else if (kout == 1) native_race_kernel<NV4, kExact, 1><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out, wc);
+    else native_race_kernel<NV4, kExact, 2><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out, wc);
 }
 
 cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, unsigned long long n_sims,
                           unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
-                          unsigned long long trace_first, unsigned long long trace_count, int sm_count, cudaStream_t st) {
+                          unsigned long long trace_first, unsigned long long trace_count, unsigned long long* work_counter,
+                          int sm_count, cudaStream_t st) {
     const int kout = trace ? 2 : (finish != nullptr || times != nullptr) ? 1 : 0;
     // persistent-style grid: MCGP_MIN_BLOCKS resident blocks per SM, split evenly over the races of the batch
     const long long resident = (long long)sm_count * MCGP_MIN_BLOCKS;
@@ -558,12 +572,13 @@ cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, u
     const dim3 grid((unsigned)bpr, n_races), block(kThreads);
     const PhiloxKeys key = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
     const NativeOutputs out{finish, times, trace, trace_first, trace ? trace_count : 0ull};
+    init_work_counters<<<1, 32, 0, st>>>(work_counter, n_races, (unsigned long long)bpr * kWarpsPerBlock);
     if (max_n <= 20) {
-        if (exact) launch_out<5, true>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out);
-        else launch_out<5, false>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out);
+        if (exact) launch_out<5, true>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out, work_counter);
+        else launch_out<5, false>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out, work_counter);
     } else {
-        if (exact) launch_out<8, true>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out);
-        else launch_out<8, false>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out);
+        if (exact) launch_out<8, true>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out, work_counter);
+        else launch_out<8, false>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out, work_counter);
     }
     return cudaGetLastError();
 }
