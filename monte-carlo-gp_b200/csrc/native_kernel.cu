@@ -34,7 +34,10 @@ namespace mcgp {
 #ifndef MCGP_MIN_BLOCKS
 #define MCGP_MIN_BLOCKS 4  // resident 256-thread blocks per SM the register budget is tuned for
 #endif
-constexpr int kWarpsPerBlock = 8;
+#ifndef MCGP_WARPS_PER_BLOCK
+#define MCGP_WARPS_PER_BLOCK 8
+#endif
+constexpr int kWarpsPerBlock = MCGP_WARPS_PER_BLOCK;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned FULL = 0xffffffffu;
 
