@@ -186,9 +186,9 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     // cumulative event thresholds (red | SC | VSC share one draw); only the event lane ever sees a non-zero ev_any
     const int ev_lane = kSmall ? 31 : 0;
     const uint32_t red_thr = R.red_thr, sc_thr = R.sc_thr;
-    const uint32_t ev_any = (!kSmall || lane == ev_lane) ? R.vsc_thr : 0u;
+    uint32_t ev_any = (!kSmall || lane == ev_lane) ? R.vsc_thr : 0u;
+    asm volatile("" : "+r"(ev_any));  // keep it a per-lane register: one compare per lap instead of compare + lane test
     const uint32_t stream = __shfl_sync(FULL, R.stream, 0);
-    const int lend_lane = 20 + (lane < 10 ? lane : lane < 20 ? lane - 10 : 0);  // kSmall: whose spare words this lane borrows
     const Tables tab{&R, lane};
 
     // Sims are handed out dynamically: a warp's first sim is its global warp index, every further one is claimed from
@@ -208,6 +208,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             slot = R.fixed_slot[lane];
         } else {
             const uint4 wg = philox4x32_10(sim_lo, sim_hi, (uint32_t)lane, stream, key);
+            const float ug = __fmul_rn((float)(wg.x >> 8), 5.9604644775390625e-08f);  // lane p holds position p's uniform
             bool remaining = is_car;
             for (int pos = 0; pos < n; pos++) {
                 float p = remaining ? R.grid[pos][lane] : 0.0f;
@@ -218,7 +219,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                     if (lane >= d) c = __fadd_rn(c, v);
                 }
                 const float total = __shfl_sync(FULL, c, 31);
-                const float u = __fmul_rn((float)(__shfl_sync(FULL, wg.x, pos) >> 8), 5.9604644775390625e-08f);
+                const float u = __shfl_sync(FULL, ug, pos);
                 const uint32_t rem_mask = __ballot_sync(FULL, remaining);
                 int sel;
                 if (total > 0.0f) {  // :125-126 (+ np.random.choice :137)
@@ -448,8 +449,10 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 if (!have_rank) full_rank(op32);
                 const float delta = __fadd_rn(prev.y, -opb);  // pace_ahead - pace_behind (+ drs_delta), x 2^15
                 // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling)
-                const bool succ = delta > ovt32 && (float)u16 < fminf(32768.0f, delta);
-                const uint32_t M = __reduce_or_sync(FULL, succ ? bit : 0u);
+                uint32_t mine;  // bit if this car overtakes the one ahead: two chained compares and ONE select
+                asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f32 p, %1, %2;\n\tsetp.lt.and.f32 q, %3, %4, p;\n\tselp.u32 %0, %5, 0, q;\n\t}"
+                    : "=r"(mine) : "f"(delta), "f"(ovt32), "f"((float)u16), "f"(fminf(32768.0f, delta)), "r"(bit));
+                const uint32_t M = __reduce_or_sync(FULL, mine);
                 if (M == 0u) return false;
                 // closed form of the sequential re-write chain :522-531 over runs of consecutive successes: with j the
                 // run start, k = rank - j and sn = "the car behind me succeeds too", the car ends on
@@ -480,32 +483,28 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         // the next); z -> this lap's overtake passes 1, 2; w -> the next lap's; passes 3 come from a borrowed word.
         // Event lane (31, or the virtual lane 64 when there are more than 20 cars): x, y -> the event draws of the
         // two laps, z -> the two 16-bit VSC roll-back draws.
-        float z_nx = 0.0f;
-        uint32_t u12_nx = 0u, u3_nx = 0u, ev_nx = 0u, roll_nx = 0u;
+        float z = 0.0f, z_nx = 0.0f;                       // this lap's / the next lap's pace noise
+        uint32_t u12 = 0u, u12_nx = 0u, ext = 0u;          // passes 1, 2 (this / next lap); low half of ext: pass 3
+        uint32_t evw = 0u, ev_nx = 0u, evz = 0u;           // event draw (this / next lap); low half of evz: roll-back draw
 #pragma unroll 1
         for (int lap = 2; lap <= L; lap++) {
-            float z;
-            uint32_t u12, u3, evw, roll;
             if ((lap & 1) == 0) {
                 const uint4 w = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)lane, stream, key);
-                uint32_t extra;
                 uint4 ev = w;
                 if (kSmall) {  // lanes 20..29 lend x (to drivers 0..9) and y (to drivers 10..19)
-                    const uint32_t e1 = __shfl_sync(FULL, w.x, lend_lane), e2 = __shfl_sync(FULL, w.y, lend_lane);
-                    extra = lane < 10 ? e1 : e2;
+                    const uint32_t e1 = __shfl_down_sync(FULL, w.x, 20), e2 = __shfl_down_sync(FULL, w.y, 10);
+                    ext = lane < 10 ? e1 : e2;
                 } else {  // up to 32 cars: a second call per lane, and one warp-uniform call for the events
-                    extra = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)(lane + 32), stream, key).x;
+                    ext = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)(lane + 32), stream, key).x;
                     ev = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 64u, stream, key);
                 }
                 if (kExact) exact_normal2(w.x, w.y, z, z_nx); else fast_normal2(w.x, w.y, z, z_nx);
                 u12 = w.z; u12_nx = w.w;
-                u3 = extra & 0xffffu; u3_nx = extra >> 16;
-                evw = ev.x; ev_nx = ev.y;
-                roll = ev.z & 0xffffu; roll_nx = ev.z >> 16;
-            } else {
-                z = z_nx; u12 = u12_nx; u3 = u3_nx; evw = ev_nx; roll = roll_nx;
+                evw = ev.x; ev_nx = ev.y; evz = ev.z;
             }
-            run_lap(lap, z, u12, u3, evw, roll);
+            run_lap(lap, z, u12, ext & 0xffffu, evw, evz & 0xffffu);
+            // hand the second half of the pair's draws to the odd lap (overwritten by the next call otherwise)
+            z = z_nx; u12 = u12_nx; ext >>= 16; evw = ev_nx; evz >>= 16;
         }
         const bool dnf = L >= dnf_lap;
         const int pos_live = live_position(!dnf);
