@@ -17,10 +17,11 @@ struct NativeRace {
     uint32_t stream;
     int32_t grid_fixed;   // 1: grid_probs is a deterministic permutation, fixed_slot[] is the grid
     int32_t _pad;
-    float pit_loss, ovt_delta, drs_delta, dirty_thr, dirty_pen;
+    float pit_loss, drs_delta, dirty_thr, dirty_pen;
+    float ovt32, drs32;                      // overtake_delta and drs_delta x 2^15 (exact): the overtake test runs on x 2^15 paces
     uint32_t red_thr, sc_thr, vsc_thr;       // CUMULATIVE floor(P * 2^32): red if w < red_thr, else SC if w < sc_thr, else VSC if w < vsc_thr
-    float pace[MCGP_LANES];                  // base_pace
-    float deg_ovt[MCGP_LANES];               // raw tire_deg (overtake pace, src/simulation.py:514)
+    float pace32[MCGP_LANES];                // base_pace x 2^15
+    float deg32[MCGP_LANES];                 // raw tire_deg x 2^15 (overtake pace, src/simulation.py:514)
     float sigma[MCGP_LANES];                 // driver_variance
     float dnf_scale[MCGP_LANES];             // 1 / ln(1 - dnf_rate) <= 0: retirement lap = 2 + floor(ln(u) * dnf_scale);
                                              // MCGP_DNF_NEVER for rate <= 0 (laps >= 2, src/simulation.py:190-197)

@@ -112,7 +112,8 @@ static void derive_native(const mcgp_race_params* r, NativeRace* o) {
     const int n = r->n_drivers;
     o->n = n; o->total_laps = r->total_laps; o->track = r->track_condition;
     o->pop_no_medium = r->pop_no_medium; o->pop_no_soft = r->pop_no_soft; o->stream = r->stream;
-    o->pit_loss = (float)r->pit_loss; o->ovt_delta = (float)r->overtake_delta; o->drs_delta = (float)r->drs_delta;
+    o->pit_loss = (float)r->pit_loss; o->drs_delta = (float)r->drs_delta;
+    o->ovt32 = (float)r->overtake_delta * 32768.0f; o->drs32 = (float)r->drs_delta * 32768.0f;
     o->dirty_thr = (float)r->dirty_air_threshold; o->dirty_pen = (float)r->dirty_air_penalty;
     {   // red flag, else SC, else VSC (:168-176): one draw against the cumulative probabilities
         const double pr = clamp01(r->red_flag_probability), ps = clamp01(r->sc_probability), pv = clamp01(r->vsc_probability);
@@ -124,8 +125,8 @@ static void derive_native(const mcgp_race_params* r, NativeRace* o) {
     }
     for (int d = 0; d < MCGP_LANES; d++) {
         const bool car = d < n;
-        o->pace[d] = car ? (float)r->base_pace[d] : 0.0f;
-        o->deg_ovt[d] = car ? (float)r->tire_deg[d] : 0.0f;
+        o->pace32[d] = car ? (float)r->base_pace[d] * 32768.0f : 0.0f;
+        o->deg32[d] = car ? (float)r->tire_deg[d] * 32768.0f : 0.0f;
         o->sigma[d] = car ? (float)r->driver_variance[d] : 0.0f;
         o->dnf_scale[d] = car ? dnf_scale(r->dnf_rate[d]) : MCGP_DNF_NEVER;
         o->lap1_thr[d] = car ? prob_threshold(r->team_dnf_rate[d] * 4.0) : 0u;  // LAP_1_DNF_MULTIPLIER :282

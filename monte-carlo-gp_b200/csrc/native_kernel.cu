@@ -177,11 +177,11 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     const float park_t = __fmul_rn(1e30f, (float)(lane + 1));
     const int park = (NV4 == 5 && lane >= 20) ? lane - 20 : 0;
     // overtake paces are carried pre-scaled by 2^15 (exact) so that the 16-bit uniform compares against them directly
-    const float pace32 = __fmul_rn(R.pace[lane], 32768.0f), deg32 = __fmul_rn(R.deg_ovt[lane], 32768.0f), sigma = R.sigma[lane];
+    const float pace32 = R.pace32[lane], deg32 = R.deg32[lane], sigma = R.sigma[lane];
     const float dnf_scale = R.dnf_scale[lane];
     const uint32_t lap1_thr = R.lap1_thr[lane];
     const float pit_loss = R.pit_loss, drs_delta = R.drs_delta;
-    const float ovt32 = __fmul_rn(R.ovt_delta, 32768.0f), drs32_on = __fmul_rn(R.drs_delta, 32768.0f);
+    const float ovt32 = R.ovt32, drs32_on = R.drs32;
     const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
     // cumulative event thresholds (red | SC | VSC share one draw); only the event lane ever sees a non-zero ev_any
     const int ev_lane = kSmall ? 31 : 0;
@@ -220,19 +220,22 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 }
                 const float total = __shfl_sync(FULL, c, 31);
                 const float u = __shfl_sync(FULL, ug, pos);
-                const uint32_t rem_mask = __ballot_sync(FULL, remaining);
-                int sel;
-                if (total > 0.0f) {  // :125-126 (+ np.random.choice :137)
-                    const float target = __fmul_rn(u, total);
-                    const uint32_t m = __ballot_sync(FULL, remaining && p > 0.0f && c > target);
-                    sel = m ? (__ffs(m) - 1) : (31 - __clz(rem_mask));
-                } else {  // :127-130 uniform over the remaining drivers
-                    const int nrem = __popc(rem_mask);
-                    int k = (int)__fmul_rn(u, (float)nrem);
-                    k = k < nrem - 1 ? k : nrem - 1;
-                    uint32_t m = rem_mask;
-                    for (int i = 0; i < k; i++) m &= m - 1;
-                    sel = __ffs(m) - 1;
+                // np.random.choice (:137): the first lane whose inclusive sum exceeds u * total -- that lane is
+                // necessarily a remaining driver with p > 0 (a lane that adds nothing cannot be the first to exceed)
+                const uint32_t m = __ballot_sync(FULL, c > __fmul_rn(u, total));
+                int sel = __ffs(m) - 1;
+                if (m == 0u) {  // rare: total == 0 (:127-130, uniform over the remaining drivers) or u * total rounded up to total
+                    const uint32_t rem_mask = __ballot_sync(FULL, remaining);
+                    if (total > 0.0f) {
+                        sel = 31 - __clz(rem_mask);
+                    } else {
+                        const int nrem = __popc(rem_mask);
+                        int k = (int)__fmul_rn(u, (float)nrem);
+                        k = k < nrem - 1 ? k : nrem - 1;
+                        uint32_t mm = rem_mask;
+                        for (int i = 0; i < k; i++) mm &= mm - 1;
+                        sel = __ffs(mm) - 1;
+                    }
                 }
                 if (lane == sel) { slot = pos; remaining = false; }
             }
