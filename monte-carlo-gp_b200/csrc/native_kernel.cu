@@ -76,6 +76,18 @@ __device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, fl
     asm volatile("st.volatile.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
+// index of the highest / lowest set bit (x != 0): FLO, resp. BREV + FLO.SH, without the compiler's 31 - clz detour
+__device__ __forceinline__ int msb(uint32_t x) {
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ int lsb(uint32_t x) {
+    int r;
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(__brev(x)));
+    return r;
+}
+
 // 1.0f iff a < b: a single FSET.BF on sm_100 (the integer-mask form costs FSETP + SEL)
 __device__ __forceinline__ float lt_one(float a, float b) {
     float m;
@@ -317,7 +329,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             bool has_pred = live && !pd;
             float tl, t_pred = prev.x, last_pred = prev.z;
             if (__popc(B) == 1) {
-                tl = __shfl_sync(FULL, t, 31 - __clz(B));
+                tl = __shfl_sync(FULL, t, msb(B));
             } else if (B) {  // retired cars sit between runners (the lap of a retirement): search the live mask
                 const uint32_t LM = __reduce_or_sync(FULL, live ? bit : 0u);
                 tl = lds_f<0>(rec_sh + 16u * (uint32_t)(__ffs(LM) - 1));
@@ -433,10 +445,11 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             // overtake pace (x 2^15); NaN for a retired car blocks both pairs it sits in (Q5)
             const float op32 = dnf ? kNaN : __fmaf_rn(age, deg32, pace32);
             const float opb = __fadd_rn(op32, -drs32);  // as the chasing car: DRS helps (:517-518)
-            // First ordering of the lap.  `rank` still holds last lap's order; in 4 laps of 5 no car has moved more
-            // than two places, so count crossings against the two old neighbours on each side only, then verify
-            // (strictly sorted + a permutation) and fall back to the full count otherwise.
-            {
+            // Re-ordering from a good guess.  `rank` holds an order in which few cars are off by more than two places
+            // (last lap's order after the lap times were added: true on 4 laps of 5; a run reversal that leapfrogged a
+            // neighbour): count crossings against the two neighbours on each side only, then verify (a permutation +
+            // strictly sorted); the caller falls back to the full count otherwise.
+            auto window_place = [&]() {
                 const uint32_t wa = w_sh + 4u * (uint32_t)rank;
                 sts_f<0>(wa, t);
                 const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
@@ -446,7 +459,8 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 const uint32_t cover = __reduce_or_sync(FULL, bit);
                 prev = lds_f4<-16>(ra);
                 have_rank = cover == FULL && !__any_sync(FULL, !(prev.x < t));
-            }
+            };
+            window_place();  // first ordering of the lap
             // one pass; returns true when another pass may follow
             auto one_pass = [&](const uint32_t u16) -> bool {
                 if (!have_rank) full_rank(op32);
@@ -461,7 +475,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 // run start, k = rank - j and sn = "the car behind me succeeds too", the car ends on
                 // T[j] - 0.1 (k + sn) + 0.3 sn = T[j] - 0.1 (k - 2 sn); a car outside every run has k = sn = 0.
                 const uint32_t clear_below = ~M & ((bit << 1) - 1u);
-                const int j = 31 - __clz(clear_below);  // run start (bit 0 of M is never set)
+                const int j = msb(clear_below);  // run start (bit 0 of M is never set)
                 const uint32_t above = ~((M >> rank) >> 1);  // bit i clear <=> pair (rank+i, rank+i+1) swapped
                 const int sn = (int)(~above & 1u);
                 const float base = lds_f<0>(rec_sh + 16u * (uint32_t)j);
@@ -469,10 +483,11 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 // The new order is almost always the old one with every run [j, e] reversed (the re-written times
                 // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
                 // Verify the presumed order with one neighbour compare instead of re-counting all ranks.
-                set_rank(j + (__ffs(above) - 1));  // j + e - rank with e = rank + ffs(above) - 1 the run end
+                set_rank(j + lsb(above));  // j + e - rank with e = rank + lsb(above) the run end
                 sts_f4<0>(ra, t, op32, last, 0.0f);
                 prev = lds_f4<-16>(ra);
                 have_rank = !__any_sync(FULL, !(prev.x < t));
+                if (!have_rank) window_place();  // second chance before counting all ranks
                 return true;
             };
             if (one_pass(u12 & 0xffffu))
