@@ -171,7 +171,9 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
 
     // warp-uniform values are broadcast from lane 0 so that the compiler can PROVE them uniform: every loop bound
     // and branch below is then convergent and the warp collectives need no divergence guards (BRA.DIV/WARPSYNC)
-    const int lane = threadIdx.x & 31, warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
+    int lane = threadIdx.x & 31;
+    asm volatile("" : "+r"(lane));  // pin it to a register: under pressure the compiler re-reads SR_TID + masks per use
+    const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
     const float kInf = __int_as_float(0x7f800000), kNaN = __int_as_float(0x7fc00000);
     float* S_t = S_t_all[warp];
     float* W = S_w_all[warp] + 8;   // W[-8..-1] = -inf, W[0..32) = times by rank, W[32..40) = +inf: no index guards needed
@@ -181,6 +183,8 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     if (lane < 2) REC[lane - 2] = make_float4(-kInf, kNaN, 0.0f, 0.0f);
     __syncwarp();
     const uint32_t w_sh = smem_u32(W), rec_sh = smem_u32(REC);
+    uint32_t grid_sh = smem_u32(&R.grid[0][lane]);
+    asm volatile("" : "+r"(grid_sh));  // (kept in a register: recomputing a shared-window address costs 6 instructions)
     const int n = __shfl_sync(FULL, R.n, 0), L = __shfl_sync(FULL, R.total_laps, 0), track = __shfl_sync(FULL, R.track, 0);
     const bool grid_fixed = __shfl_sync(FULL, R.grid_fixed, 0) != 0;
     const bool is_car = lane < n;
@@ -222,8 +226,9 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             const uint4 wg = philox4x32_10(sim_lo, sim_hi, (uint32_t)lane, stream, key);
             const float ug = __fmul_rn((float)(wg.x >> 8), 5.9604644775390625e-08f);  // lane p holds position p's uniform
             bool remaining = is_car;
-            for (int pos = 0; pos < n; pos++) {
-                float p = remaining ? R.grid[pos][lane] : 0.0f;
+            uint32_t ga = grid_sh;  // &R.grid[pos][lane] as a 32-bit shared address: one add per position
+            for (int pos = 0; pos < n; pos++, ga += 4u * MCGP_LANES) {
+                float p = remaining ? lds_f<0>(ga) : 0.0f;
                 float c = p;  // inclusive Hillis-Steele scan over lanes (the mirror replays this exact tree)
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
