@@ -187,3 +187,27 @@ def test_trace_equals_cpu_mirror(mcgp, oracle, case):
     pos = trace[0]["position"]
     live = pos > 0
     assert (np.sort(np.where(live, pos, 255), axis=2)[..., 0] == np.where(live.any(2), 1, 255)).all()
+
+
+@pytest.mark.parametrize("n,laps", [(32, 40), (21, 33), (13, 20), (2, 12)])
+def test_exact_mode_other_field_sizes(mcgp, oracle, n, laps):
+    """Field sizes around the kernel's two variants (<= 20 cars: spare lanes lend draws; up to 32: a full warp, no
+    spare lane): every finishing order and final gap equals the scalar mirror."""
+    wl = mcgp.workloads
+    D = [f"D{i:02d}" for i in range(n)]
+    teams = list(wl.DEFAULT_DNF_RATES)
+    cfg = wl.race_config_kwargs(dict(laps=laps, pit_loss=21.0, drs_zones=2, overtake_delta=0.5),
+                                dict(sc_probability=0.03, vsc_probability=0.03, red_flag_probability=0.01),
+                                driver_teams={d: teams[i % len(teams)] for i, d in enumerate(D)})
+    mc = wl.common_inputs(laps, D)
+    mc["driver_dnf_rates"] = {d: 0.004 for d in D}
+    eng = mcgp.capi.get_engine(0)
+    n_sims = 20000
+    hist, finish, times = eng.run_native([_params(mcgp, cfg, mc, stream=1)], n_sims, sim_begin=5, seed=31337,
+                                         flags=mcgp.capi.F_EXACT_NORMAL, want_finish=True, want_times=True)
+    ref = oracle.run_native(oracle.make_params(cfg, mc, *POP), 31337, n_sims, sim_begin=5, stream=1, exact=True, detail=True,
+                            threads=8)
+    bad = np.nonzero((finish[0] != ref["finish"]).any(1))[0]
+    assert bad.size == 0, f"{bad.size} of {n_sims} races differ from the CPU mirror, first: sim {bad[:5]}"
+    assert np.array_equal(times[0].view(np.uint32), ref["times"].view(np.uint32))
+    assert np.array_equal(hist[0].astype(np.int64), ref["hist"])
