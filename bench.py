@@ -291,6 +291,49 @@ def main():
         except Exception as e:  # the replay figure is auxiliary; never lose the headline line over it
             replay = {"error": repr(e)}
 
+    # ---- BASELINE configs 4 and 5, reported beside the headline (rank 0, same device-timed method) -----
+    aux = {}
+    if rank == 0:
+        try:
+            eng = sharded.engine
+            st = torch.cuda.current_stream().cuda_stream
+
+            def timed(fn, reps=3):
+                fn(); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    fn()
+                b.record(); torch.cuda.synchronize()
+                return a.elapsed_time(b) / reps
+            # config 4: the 24-race season in ONE launch (one block column per race, 24 count tables)
+            wl = mcgp.workloads
+            plist = []
+            for r in range(wl.N_SEASON_RACES):
+                c4, m4 = wl.workload(f"season:{r}")
+                s4 = mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**c4), device=local, pop_no_medium="SOFT", pop_no_soft="MEDIUM")
+                plist.append(s4._params(m4["grid_probs"], m4["base_pace"], m4["tire_deg"], m4["driver_variance"],
+                                        m4["driver_dnf_rates"], m4["track_condition"], stream=r))
+            eng.upload_races(plist)
+            n4 = max(1, S // 24)
+            h4 = torch.zeros((len(plist), N_DRIVERS, N_DRIVERS), dtype=torch.int64, device=dev)
+            ms = timed(lambda: eng.launch_native(n4, 0, seed, h4.data_ptr(), stream=st))
+            laps4 = sum(p.total_laps for p in plist)
+            aux["season_batch"] = {"races_in_batch": len(plist), "sims_per_race": n4, "races_per_s": len(plist) * n4 / (ms * 1e-3),
+                                   "driver_laps_per_s": n4 * laps4 * N_DRIVERS / (ms * 1e-3), "ms": ms}
+            # config 5: per-lap trace of every sim (8 B per driver-lap) -- the variant that writes to HBM
+            eng.upload_races([params])
+            n5 = min(S, 4_000_000)
+            tr = torch.empty(n5 * LAPS * N_DRIVERS * 8, dtype=torch.uint8, device=dev)
+            h5 = torch.zeros((1, N_DRIVERS, N_DRIVERS), dtype=torch.int64, device=dev)
+            ms = timed(lambda: eng.launch_native_traced(n5, 0, seed, h5.data_ptr(), tr.data_ptr(), 0, n5, stream=st))
+            aux["trace_mode"] = {"sims": n5, "races_per_s": n5 / (ms * 1e-3), "trace_bytes_per_race": LAPS * N_DRIVERS * 8,
+                                 "hbm_write_gb_per_s": n5 * LAPS * N_DRIVERS * 8 / (ms * 1e-3) / 1e9, "ms": ms}
+            del tr
+            eng.upload_races([params])
+        except Exception as e:  # auxiliary figures; never lose the headline line over them
+            aux["error"] = repr(e)
+
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only) --------------------------------
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -335,7 +378,10 @@ def main():
                                  + NCU["capture"] + ") x races/s / peak; traffic = dram bytes read+written per launch (ncu)"},
             "cpu_baseline": cpu,
             "replay_mode": replay,
+            "season_batch": aux.get("season_batch"), "trace_mode": aux.get("trace_mode"),
         }
+        if "error" in aux:
+            line["aux_error"] = aux["error"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

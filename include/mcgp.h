@@ -87,7 +87,7 @@ const char* mcgp_last_error(mcgp_handle h);
 /* multiProcessorCount and current SM clock (kHz) of the context's device, for roofline arithmetic. */
 int mcgp_device_info(mcgp_handle h, int* sm_count, int* sm_clock_khz, int* cc_major, int* cc_minor);
 
-/* native mode: counter-based Philox4x32-10 keyed (seed ; sim, lap, driver, stream), FP32 ------- *
+/* native mode: counter-based Philox4x32-10 keyed (seed ; sim, lap pair, lane, stream), FP32 ----- *
  * Replaces the loop of run_monte_carlo (src/simulation.py:83-94) for sims
  * [sim_begin, sim_begin + n_sims) of each of the n_races races; results do not depend on how a sim
  * range is split over calls or GPUs.

@@ -160,7 +160,18 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     __shared__ float S_w_all[kWarpsPerBlock][48];              // window scratch: times by OLD rank, -inf / +inf pads
     __shared__ __align__(16) float4 S_rec_all[kWarpsPerBlock][36];  // records by rank: {time, overtake pace, last lap, lane}
 
-    const int race = blockIdx.y;
+    // A block starts on race blockIdx.y of the batch and, when that race's sims are all claimed, hops to the next
+    // race that still has work (a season batch mixes 44- and 78-lap races: without hopping the blocks of the short
+    // races idle while the long ones finish).  One hop = reload the 7 KB parameter block, flush the count table.
+    __shared__ int more_work;
+    for (int hop = 0; hop < (int)gridDim.y; hop++) {
+    const int race = (int)((blockIdx.y + hop) % gridDim.y);
+    if (hop > 0) {
+        __syncthreads();  // everybody is done with R and hist_s of the previous race
+        if (threadIdx.x == 0) more_work = *reinterpret_cast<volatile unsigned long long*>(work_counter + race) < n_sims;
+        __syncthreads();
+        if (!more_work) continue;
+    }
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(races + race);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&R);
@@ -212,7 +223,12 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     // of its use.  The warp scheduler favours some warps over others, so an even static split left 20 % of the
     // warp-slots idle at the end; which warp runs which sim does not matter (draws are keyed by the sim index).
     unsigned long long* const claim = work_counter + race;
-    for (unsigned long long s = (unsigned long long)blockIdx.x * kWarpsPerBlock + (unsigned)warp; s < n_sims;) {
+    unsigned long long s = (unsigned long long)blockIdx.x * kWarpsPerBlock + (unsigned)warp;  // static first sim on the home race
+    if (hop > 0) {
+        if (lane == 0) s = atomicAdd(claim, 1ull);
+        s = __shfl_sync(FULL, s, 0);
+    }
+    while (s < n_sims) {
         unsigned long long s_next = 0;
         if (lane == 0) s_next = atomicAdd(claim, 1ull);
         const unsigned long long sim = sim_begin + s;
@@ -565,6 +581,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         const uint32_t v = hist_s[i];
         if (v) atomicAdd(&hist[(unsigned long long)race * n * n + i], (unsigned long long)v);
     }
+    }  // hop
 }
 
 // every race's claim counter starts behind the statically assigned first sims
@@ -590,7 +607,7 @@ cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, u
     const int kout = trace ? 2 : (finish != nullptr || times != nullptr) ? 1 : 0;
     // persistent-style grid: MCGP_MIN_BLOCKS resident blocks per SM, split evenly over the races of the batch
     const long long resident = (long long)sm_count * MCGP_MIN_BLOCKS;
-    long long bpr = (resident + n_races - 1) / n_races;
+    long long bpr = resident / n_races;  // (never more blocks than fit at once: a waiting block could only start late)
     const long long need = (long long)((n_sims + kWarpsPerBlock - 1) / kWarpsPerBlock);
     if (bpr > need) bpr = need;
     if (bpr < 1) bpr = 1;
