@@ -211,3 +211,19 @@ def test_exact_mode_other_field_sizes(mcgp, oracle, n, laps):
     assert bad.size == 0, f"{bad.size} of {n_sims} races differ from the CPU mirror, first: sim {bad[:5]}"
     assert np.array_equal(times[0].view(np.uint32), ref["times"].view(np.uint32))
     assert np.array_equal(hist[0].astype(np.int64), ref["hist"])
+
+
+def test_pipeline_from_ratings_matches_reference_statistics(mcgp, oracle):
+    """SURVEY 8(f) rank 2 end to end: Elo ratings -> grid_model.grid_probabilities (np.float64 rows with a grid penalty) ->
+    native simulation, against the FP64 oracle fed the same rows."""
+    cfg, mc = mcgp.workloads.workload("bahrain")
+    D = list(mc["grid_probs"])
+    mc = dict(mc, grid_probs=mcgp.grid_model.grid_probabilities(
+        D, {d: 1500.0 + 35.0 * (9.5 - k) for k, d in enumerate(D)},
+        features={D[2]: {"teammate_delta": 1.5, "form_score": 0.8}, D[5]: {"circuit_affinity": -0.7}},
+        penalties={D[0]: "gearbox", D[6]: "engine"}))
+    sim = _sim(mcgp, cfg)
+    args = [mc.get(k) for k in MC_KEYS]
+    print(assert_agree_two_stage(lambda n, st: sim.run_monte_carlo_counts(n, *args, seed=300 + st),
+                                 lambda n, st: oracle.run_monte_carlo(cfg, mc, n, 4321 + st, *POP, threads=8),
+                                 2000000, 200000, "ratings pipeline"))
