@@ -78,3 +78,20 @@ if __name__ == "__main__":
     with open(path, "w") as f:
         json.dump(golden, f, indent=0)
     print(path, len(golden), "cases", os.path.getsize(path), "bytes")
+
+    # a synthetic season of qualifying / race events through the reference's F1EloSystem (src/elo.py)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, REF)
+    from src.elo import F1EloSystem
+    sys.path.remove(REF)
+    import test_ratings
+    import mcgp_b200
+    D = list(mcgp_b200.workloads.DRIVER_TEAMS)
+    events = test_ratings._events(random.Random(2025), D, 48)
+    elo = F1EloSystem()
+    ratings = test_ratings._apply(elo, events)
+    pole = {d: float(v).hex() for d, v in elo.predict_quali_probs(D).items()}
+    path = os.path.join(ROOT, "tests", "golden", "ratings.json")
+    with open(path, "w") as f:
+        json.dump(dict(drivers=D, events=events, ratings=ratings, pole=pole), f, indent=0)
+    print(path, len(events), "events", os.path.getsize(path), "bytes")
