@@ -250,26 +250,26 @@ def main():
     d2h = N_DRIVERS * N_DRIVERS * 8
 
     # ---- replay mode (BASELINE config 2), reported beside the headline ----------------------------
-    # Tapes: NumPy's own legacy MT19937 stream (the generator behind the reference's np.random.* calls), cut
-    # into per-sim slices of the worst-case draw count (4556 U_py / 1160 Z / 20 U_np at n=20, L=57).
+    # Throughput only (bit-exactness is tests/ and tools/replay_config2.py): synthetic uniform / normal tapes made
+    # on the device, cut into per-sim slices of the worst-case draw count (4556 U_py / 1160 Z / 20 U_np).
     replay = None
     if rank == 0:
         try:
             import numpy as np
-            n_rep = 8000
+            n_rep = 100_000   # enough races to fill the GPU (21 per resident warp); ~3.7 GB of synthetic tapes
             n_py = N_DRIVERS + (LAPS - 1) * (4 + N_DRIVERS + 3 * (N_DRIVERS - 1))
             n_z = 2 * N_DRIVERS + (LAPS - 1) * N_DRIVERS
-            rs = np.random.RandomState(42)
-            tapes = [torch.from_numpy(rs.random_sample(n_rep * n_py)).to(dev),
-                     torch.from_numpy(rs.standard_normal(n_rep * n_z)).to(dev),
-                     torch.from_numpy(rs.random_sample(n_rep * N_DRIVERS)).to(dev)]
+            g = torch.Generator(device=dev).manual_seed(42)
+            tapes = [torch.rand(n_rep * n_py, dtype=torch.float64, device=dev, generator=g),
+                     torch.randn(n_rep * n_z, dtype=torch.float64, device=dev, generator=g),
+                     torch.rand(n_rep * N_DRIVERS, dtype=torch.float64, device=dev, generator=g)]
             off = torch.from_numpy(np.arange(n_rep + 1, dtype=np.int64)[:, None] * np.array([n_py, n_z, N_DRIVERS], np.int64)).contiguous().to(dev)
             rh = torch.zeros((N_DRIVERS, N_DRIVERS), dtype=torch.int64, device=dev)
             used = torch.zeros((n_rep, 3), dtype=torch.int64, device=dev)
             status = torch.zeros(4, dtype=torch.int32, device=dev)
             eng = sharded.engine
             st = torch.cuda.current_stream().cuda_stream
-            reps = 8
+            reps = 3
 
             def go():
                 eng.launch_replay(n_rep, tapes[0].data_ptr(), tapes[1].data_ptr(), tapes[2].data_ptr(), off.data_ptr(),

@@ -19,8 +19,8 @@ cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, u
                           int sm_count, cudaStream_t st);
 cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
-                          double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status, int sm_count,
-                          cudaStream_t st);
+                          double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
+                          unsigned long long* work_counter, int sm_count, cudaStream_t st);
 }  // namespace mcgp
 
 struct mcgp_context {
@@ -352,8 +352,8 @@ int mcgp_launch_replay(mcgp_handle h, uint64_t n_sims, const double* u_py_dev, c
     CU(cudaSetDevice(h->device));
     CU(mcgp::launch_replay(h->replay_dev, n_sims, u_py_dev, z_dev, u_np_dev, (const long long*)off_dev,
                            (unsigned long long*)hist_dev, finish_dev, times_dev, dnf_lap_dev, grid_dev,
-                           (long long*)used_dev, status_dev, h->sm_count, (cudaStream_t)cuda_stream));
-    h->launches = 1;
+                           (long long*)used_dev, status_dev, h->work_counter, h->sm_count, (cudaStream_t)cuda_stream));
+    h->launches = 2;  // the claim-counter reset + the replay kernel
     return MCGP_OK;
 }
 

@@ -15,6 +15,8 @@
 
 namespace mcgp {
 
+__global__ void init_work_counters(unsigned long long* wc, int n_races, unsigned long long first);  // native_kernel.cu
+
 constexpr int kRWarps = 4;
 constexpr int kRThreads = kRWarps * 32;
 constexpr unsigned RFULL = 0xffffffffu;
@@ -90,7 +92,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                    const double* __restrict__ zt, const double* __restrict__ u_np, const long long* __restrict__ off,
                    unsigned long long* __restrict__ hist, uint8_t* __restrict__ finish, double* __restrict__ times,
                    int16_t* __restrict__ dnf_lap_out, uint8_t* __restrict__ grid_out, long long* __restrict__ used_out,
-                   int* __restrict__ status) {
+                   int* __restrict__ status, unsigned long long* __restrict__ work_counter) {
     __shared__ ReplayRace R;
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     __shared__ double S_p_all[kRWarps][32];
@@ -113,8 +115,11 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     const uint32_t lt_mask = (1u << lane) - 1u;
     int err = 0;
 
-    const unsigned long long total_warps = (unsigned long long)gridDim.x * kRWarps;
-    for (unsigned long long s = (unsigned long long)blockIdx.x * kRWarps + warp; s < n_sims; s += total_warps) {
+    // sims are claimed dynamically (counter host-initialised to the number of warps), one race ahead of their use:
+    // races differ in length (retirements, overtake passes) and the warp scheduler is priority based
+    for (unsigned long long s = (unsigned long long)blockIdx.x * kRWarps + warp; s < n_sims;) {
+        unsigned long long s_next = 0;
+        if (lane == 0) s_next = atomicAdd(work_counter, 1ull);
         Tape py{u_py, off[3 * s], off[3 * s + 3]};
         Tape zz{zt, off[3 * s + 1], off[3 * s + 4]};
         Tape np{u_np, off[3 * s + 2], off[3 * s + 5]};
@@ -399,6 +404,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 used_out[3 * s + 2] = np.i - np0;
             }
         }
+        s = __shfl_sync(RFULL, s_next, 0);
     }
     if (err && status) atomicExch(status, -4);
 
@@ -411,14 +417,15 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
 
 cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
-                          double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status, int sm_count,
-                          cudaStream_t st) {
-    long long blocks = (long long)sm_count * 8;
+                          double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
+                          unsigned long long* work_counter, int sm_count, cudaStream_t st) {
+    long long blocks = (long long)sm_count * 6;  // 80 registers x 128 threads: six blocks are resident per SM
     const long long need = (long long)((n_sims + kRWarps - 1) / kRWarps);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
+    init_work_counters<<<1, 32, 0, st>>>(work_counter, 1, (unsigned long long)blocks * kRWarps);
     replay_race_kernel<<<(unsigned)blocks, kRThreads, 0, st>>>(race_dev, n_sims, u_py, z, u_np, off, hist, finish, times,
-                                                            dnf_lap, grid, used, status);
+                                                            dnf_lap, grid, used, status, work_counter);
     return cudaGetLastError();
 }
 
