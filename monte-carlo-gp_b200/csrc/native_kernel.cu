@@ -369,19 +369,23 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             ahead_last = has_pred ? last_pred : 0.0f;  // (retired cars: 0, never read)
             t = __fadd_rn(t, -tl);  // (+inf stays +inf on lanes without a car)
         };
+        // per-lap trace (BASELINE config 5): one 8-byte record per driver per lap, 8 n contiguous bytes per warp and lap;
+        // the record pointer walks the sim's [lap][driver] block, the first word is packed with integer ops
+        uint2* tr_ptr = nullptr;
+        if (kTrace && traced)
+            tr_ptr = reinterpret_cast<uint2*>(out.trace) +
+                     ((unsigned long long)race * out.trace_count + (s - out.trace_first)) * (unsigned)L * (unsigned)n + lane;
         auto emit_trace = [&](const int lap, const bool dnf_now) {
             if (kTrace) {
-                if (traced) {  // one 8-byte record per driver per lap: 160 contiguous bytes per warp
+                if (traced) {
                     const int pl = live_position(!dnf_now);
-                    if (is_car) {
-                        TraceRecord rec;
-                        rec.position = dnf_now ? 0 : (uint8_t)(pl + 1);
-                        rec.compound = (uint8_t)comp;
-                        rec.tire_age = (uint8_t)(int)age;
-                        rec.flags = (uint8_t)((dnf_now ? 1 : 0) | (tr_drs ? 2 : 0) | (tr_pit ? 4 : 0) | (tr_event << 4));
-                        rec.gap = t;
-                        out.trace[(((unsigned long long)race * out.trace_count + (s - out.trace_first)) * (unsigned)L + (unsigned)(lap - 1)) * (unsigned)n + lane] = rec;
-                    }
+                    // byte 0 position (0 = retired), 1 compound, 2 tyre age, 3 flags (bit0 retired, bit1 DRS, bit2 pitted, bits4-5 event)
+                    uint32_t w0 = dnf_now ? 0x01000000u : (uint32_t)(pl + 1);
+                    w0 |= (uint32_t)comp << 8;
+                    w0 |= ((uint32_t)(int)age & 0xffu) << 16;
+                    w0 |= (tr_drs ? 0x02000000u : 0u) | (tr_pit ? 0x04000000u : 0u) | ((uint32_t)tr_event << 28);
+                    if (is_car) *tr_ptr = make_uint2(w0, __float_as_uint(t));
+                    tr_ptr += n;
                 }
                 tr_event = 0;
                 tr_pit = false;
