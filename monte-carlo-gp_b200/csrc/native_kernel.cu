@@ -311,7 +311,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             age = __fadd_rn(age, 1.0f);
         }
 
-        int drs_until = 0;
+        int drs_until = 2;  // DRS is off through this lap: laps 1-2 (:551), then through the laps an event disables it
         int rank;
         uint32_t bit;          // 1 << rank
         uint32_t ra;           // shared address of REC[rank]
@@ -362,7 +362,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             } else {  // nobody left running: times stay as they are
                 return;
             }
-            const bool drs_now = has_pred && lap > 2 && lap > drs_until && (__fadd_rn(t, -t_pred) < 1.0f);
+            const bool drs_now = has_pred && lap > drs_until && (__fadd_rn(t, -t_pred) < 1.0f);
             if (kTrace) tr_drs = drs_now;
             drs_f = drs_now ? drs_delta : 0.0f;
             drs32 = drs_now ? drs32_on : 0.0f;
@@ -397,12 +397,14 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         emit_trace(1, dnf_lap <= 1);
 
         // One lap >= 2.  z: this lap's pace noise; u12: overtake uniforms of passes 1 / 2 in the low / high half;
-        // u3: pass 3 (16 bits); ev: the word that decides the race event (compared on the event lane only: the
-        // thresholds are 0 on every other lane); roll: 16 bits for the VSC tyre roll-back.
-        auto run_lap = [&](const int lap, const float z, const uint32_t u12, const uint32_t u3, const uint32_t ev, const uint32_t roll) {
+        // ext: pass 3 of the pair's even / odd lap in its low / high half; ev: the word that decides the race event
+        // (compared on the event lane only: the threshold is 0 on every other lane); evz: the two 16-bit VSC
+        // tyre roll-back draws (even / odd lap).
+        auto run_lap = [&](const int lap, const float z, const uint32_t u12, const uint32_t ext, const uint32_t ev, const uint32_t evz) {
             const int rem = L - lap;
             // ---- race-interrupting events (:168-176): one draw on the cumulative thresholds ---------
             if (__any_sync(FULL, ev < ev_any)) {  // rare (2.7 % of laps with the product probabilities)
+                const uint32_t roll = (lap & 1) ? evz >> 16 : evz & 0xffffu;
                 const int code = ev < red_thr ? 1 : ev < sc_thr ? 2 : (roll < kVscRoll16 ? 4 : 3);
                 const int e = __shfl_sync(FULL, code, ev_lane);
                 const bool out_before = lap > dnf_lap;  // retired on an earlier lap (this lap's retirements still run here)
@@ -516,7 +518,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 return true;
             };
             if (one_pass(u12 & 0xffffu))
-                if (one_pass(u12 >> 16)) one_pass(u3);
+                if (one_pass(u12 >> 16)) one_pass((lap & 1) ? ext >> 16 : ext & 0xffffu);
             if (!have_rank) full_rank(op32);
             update_positions(lap, dnf);
             emit_trace(lap, dnf);
@@ -528,7 +530,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         // two laps, z -> the two 16-bit VSC roll-back draws.
         float z = 0.0f, z_nx = 0.0f;                       // this lap's / the next lap's pace noise
         uint32_t u12 = 0u, u12_nx = 0u, ext = 0u;          // passes 1, 2 (this / next lap); low half of ext: pass 3
-        uint32_t evw = 0u, ev_nx = 0u, evz = 0u;           // event draw (this / next lap); low half of evz: roll-back draw
+        uint32_t ev_even = 0u, ev_odd = 0u, evz = 0u;      // event draws of the pair's two laps; evz: the two 16-bit roll-back draws
 #pragma unroll 1
         for (int lap = 2; lap <= L; lap++) {
             if ((lap & 1) == 0) {
@@ -543,11 +545,11 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 }
                 if (kExact) exact_normal2(w.x, w.y, z, z_nx); else fast_normal2(w.x, w.y, z, z_nx);
                 u12 = w.z; u12_nx = w.w;
-                evw = ev.x; ev_nx = ev.y; evz = ev.z;
+                ev_even = ev.x; ev_odd = ev.y; evz = ev.z;
             }
-            run_lap(lap, z, u12, ext & 0xffffu, evw, evz & 0xffffu);
+            run_lap(lap, z, u12, ext, (lap & 1) ? ev_odd : ev_even, evz);
             // hand the second half of the pair's draws to the odd lap (overwritten by the next call otherwise)
-            z = z_nx; u12 = u12_nx; ext >>= 16; evw = ev_nx; evz >>= 16;
+            z = z_nx; u12 = u12_nx;
         }
         const bool dnf = L >= dnf_lap;
         const int pos_live = live_position(!dnf);
