@@ -36,16 +36,29 @@ struct Tape {
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(RFULL, v, src); }
 
-// rank of (v, lane) among lanes selected by `in_set` (warp-uniform mask), ascending, ties by lane
-__device__ __forceinline__ int rank_set(double v, uint32_t in_set, int lane) {
+// rank of (v, lane) among the lanes selected by `in_set` (warp-uniform mask), ascending, ties by lane.
+// Keys go through 32 doubles of warp scratch: every lane reads them back with broadcast LDS.128s and counts the
+// strictly smaller ones (2 instructions per key instead of a 2-shuffle round trip per key); exact ties -- possible
+// here: VSC scaling, the 0.1 s floor of the overtake re-write -- show up as a hole in the rank set and are fixed up.
+__device__ __forceinline__ int rank_set(double v, uint32_t in_set, int lane, int n, double* S_key) {
+    const bool member = (in_set >> lane) & 1u;
+    S_key[lane] = member ? v : __longlong_as_double(0x7ff0000000000000ll);
+    __syncwarp();
     int cnt = 0;
-    uint32_t m = in_set;
-    while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        const double vj = shfl_d(v, j);
-        cnt += (vj < v || (vj == v && j < lane)) ? 1 : 0;
+    const double2* k2 = reinterpret_cast<const double2*>(S_key);
+    for (int j = 0; 2 * j < n; j++) {
+        const double2 k = k2[j];
+        cnt += (k.x < v) ? 1 : 0;
+        cnt += (k.y < v) ? 1 : 0;
     }
+    const int m = __popc(in_set);
+    const uint32_t want = m >= 32 ? RFULL : ((1u << m) - 1u);
+    const uint32_t seen = __reduce_or_sync(RFULL, member ? (1u << (cnt & 31)) : 0u);
+    if (seen != want) {
+#pragma unroll 1
+        for (int j = 0; j < lane; j++) cnt += (S_key[j] == v) ? 1 : 0;
+    }
+    __syncwarp();
     return cnt;
 }
 
@@ -95,7 +108,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                    int* __restrict__ status, unsigned long long* __restrict__ work_counter) {
     __shared__ ReplayRace R;
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
-    __shared__ double S_p_all[kRWarps][32];
+    __shared__ __align__(16) double S_p_all[kRWarps][32];  // grid sampling items, then the rank keys
     __shared__ uint8_t S_k_all[kRWarps][32];
     __shared__ uint32_t S_inv_all[kRWarps][32];
     {
@@ -195,7 +208,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         // _update_positions :538-560
         auto update_positions = [&](int lap, bool drs_disabled) {
             const uint32_t live_m = __ballot_sync(RFULL, !dnf);
-            const int r = rank_set(cum, live_m, lane);
+            const int r = rank_set(cum, live_m, lane, n, S_p);
             if (!dnf) S_inv[r] = lane;
             __syncwarp();
             if (live_m) {
@@ -281,7 +294,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                         if (r4 < 0.3 && !dnf) age = age - 1 > 0 ? age - 1 : 0;
                     }
                     // :179 re-sorts after the handler; a VSC can create exact ties, so re-derive the car ahead
-                    const int r = rank_set(cum, live_m, lane);
+                    const int r = rank_set(cum, live_m, lane, n, S_p);
                     __syncwarp();
                     if (!dnf) S_inv[r] = lane;
                     __syncwarp();
@@ -340,7 +353,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             {
                 const double op = R.pace[drv] + (double)age * deg;  // :514-515 (raw driver deg)
                 for (int pass = 0; pass < 3; pass++) {
-                    const int r = rank_set(cum, nmask, lane);  // ALL cars, retired ones included (Q5)
+                    const int r = rank_set(cum, nmask, lane, n, S_p);  // ALL cars, retired ones included (Q5)
                     __syncwarp();
                     if (is_car) S_inv[r] = lane;
                     __syncwarp();
@@ -419,7 +432,7 @@ cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
                           unsigned long long* work_counter, int sm_count, cudaStream_t st) {
-    long long blocks = (long long)sm_count * 6;  // 80 registers x 128 threads: six blocks are resident per SM
+    long long blocks = (long long)sm_count * 5;  // 92 registers x 128 threads: five blocks are resident per SM
     const long long need = (long long)((n_sims + kRWarps - 1) / kRWarps);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
