@@ -159,11 +159,19 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     const int n_rem = __popc(remaining);
                     if ((remaining >> lane) & 1u) { pd = 1.0 / (double)n_rem; kd = 1; } else { pd = 0.0; kd = 0; }
                 }
-                S_p[lane] = pd; S_k[lane] = kd;
-                __syncwarp();
-                const double prob_sum = py_sum(S_p, S_k, n, tk);  // :133
-                __syncwarp();
-                if (prob_sum > 0 && fabs(prob_sum - 1.0) > 1e-9) pd = pd / prob_sum;  // :134-135
+                // :133-135 renormalise if abs(sum(probs) - 1) > 1e-9.  The exact sum() only matters when that fires:
+                // a butterfly sum is within ~1e-15 of it, so unless it lands near the threshold the (usual) answer
+                // "no renormalisation" is certain without replaying CPython's serial summation.
+                double approx = pd;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) approx += shfl_d(approx, lane ^ d);
+                if (!__all_sync(RFULL, fabs(approx - 1.0) < 1e-9 - 1e-12)) {
+                    S_p[lane] = pd; S_k[lane] = kd;
+                    __syncwarp();
+                    const double prob_sum = py_sum(S_p, S_k, n, tk);  // :133
+                    __syncwarp();
+                    if (prob_sum > 0 && fabs(prob_sum - 1.0) > 1e-9) pd = pd / prob_sum;  // :134-135
+                }
                 S_p[lane] = pd;
                 __syncwarp();
                 // p.cumsum(); cdf /= cdf[-1]; searchsorted(u, side='right')
