@@ -227,3 +227,89 @@ def test_pipeline_from_ratings_matches_reference_statistics(mcgp, oracle):
     print(assert_agree_two_stage(lambda n, st: sim.run_monte_carlo_counts(n, *args, seed=300 + st),
                                  lambda n, st: oracle.run_monte_carlo(cfg, mc, n, 4321 + st, *POP, threads=8),
                                  2000000, 200000, "ratings pipeline"))
+
+
+def _random_case(rnd):
+    """A random but valid (RaceConfig kwargs, run_monte_carlo kwargs) pair spanning the parameter space."""
+    wl = mcgp_b200_workloads()
+    n = rnd.choice([1, 2, 5, 9, 16, 19, 20, 20, 20, 21, 24, 31, 32])
+    laps = rnd.choice([1, 2, 3, 7, 19, 33, 57, 78, 90])
+    D = [f"R{i:02d}" for i in range(n)]
+    teams = list(wl.DEFAULT_DNF_RATES) + ["Unknown"]
+    compounds = {k: dict(v) for k, v in wl.TIRE_COMPOUNDS.items()}
+    for c in compounds.values():
+        c["pace_delta"] += rnd.uniform(-0.3, 0.3)
+        c["deg_rate"] *= rnd.uniform(0.5, 2.0)
+        c["optimal_laps"] = max(2, int(c["optimal_laps"] * rnd.uniform(0.3, 1.5)))
+    cfg = dict(total_laps=laps, pit_loss=rnd.uniform(12.0, 32.0), overtake_delta=rnd.choice([0.0, 0.3, 0.6, 1.5, 5.0]),
+               sc_probability=rnd.choice([0.0, 0.01, 0.08, 0.5]), vsc_probability=rnd.choice([0.0, 0.015, 0.1]),
+               red_flag_probability=rnd.choice([0.0, 0.002, 0.05]),
+               dnf_rates={t: rnd.choice([0.0, 0.002, 0.02]) for t in teams[:-1]}, drs_zones=2, drs_delta=rnd.choice([0.0, 0.3, 0.8]),
+               tire_compounds=compounds, driver_teams={d: rnd.choice(teams) for d in D})
+    kind = rnd.choice(["gauss", "gauss", "onehot", "flat", "sparse"])
+    if kind == "gauss":
+        gp = wl.gaussian_grid_probs(D, spread=rnd.uniform(0.6, 6.0))
+    elif kind == "onehot":
+        order = list(range(n)); rnd.shuffle(order)
+        gp = wl.onehot_grid_probs(D, order)
+    elif kind == "flat":
+        gp = {d: [1.0 / n] * n for d in D}
+    else:   # many exact zeros, some all-zero rows / columns: the uniform-over-remaining branch (:127-130)
+        gp = {d: [rnd.choice([0.0, 0.0, rnd.random()]) for _ in range(n)] for d in D}
+    mc = dict(grid_probs=gp, base_pace={d: 88.0 + rnd.uniform(0.0, 3.0) for d in D},
+              tire_deg={d: rnd.choice([0.0, 0.01, 0.03, 0.06, 0.12]) for d in D},
+              driver_variance={d: rnd.choice([0.0, 0.05, 0.15, 0.4]) for d in D},
+              driver_dnf_rates={d: rnd.choice([0.0, 0.05 / laps, 0.01, 0.2, 1.0]) for d in D},
+              track_condition=rnd.choice(["dry", "dry", "dry", "damp", "wet"]))
+    return cfg, mc
+
+
+def mcgp_b200_workloads():
+    import mcgp_b200
+    return mcgp_b200.workloads
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_exact_mode_random_configurations(mcgp, oracle, block):
+    """Randomised sweep of the parameter space (field size, race length, event storms, certain / impossible retirements,
+    zero variance, degenerate grids, all track conditions): the kernel must equal the scalar mirror race by race."""
+    import random
+    rnd = random.Random(1000 + block)
+    eng = mcgp.capi.get_engine(0)
+    for trial in range(8):
+        cfg, mc = _random_case(rnd)
+        n_sims, seed = 3000, rnd.getrandbits(64)
+        pop = (rnd.choice(["SOFT", "HARD"]), rnd.choice(["MEDIUM", "HARD"]))
+        sim = mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**cfg), pop_no_medium=pop[0], pop_no_soft=pop[1])
+        p = sim._params(*[mc.get(k) for k in MC_KEYS], mc["track_condition"], stream=trial)
+        hist, finish, times = eng.run_native([p], n_sims, sim_begin=trial * 7919, seed=seed, flags=mcgp.capi.F_EXACT_NORMAL,
+                                             want_finish=True, want_times=True)
+        ref = oracle.run_native(oracle.make_params(cfg, mc, *pop), seed, n_sims, sim_begin=trial * 7919, stream=trial, exact=True,
+                                detail=True, threads=8)
+        what = f"block {block} trial {trial}: n={p.n_drivers} laps={cfg['total_laps']} {mc['track_condition']}"
+        bad = np.nonzero((finish[0] != ref["finish"]).any(1))[0]
+        assert bad.size == 0, f"{what}: {bad.size} of {n_sims} races differ from the CPU mirror, first: sim {bad[:5]}"
+        assert np.array_equal(times[0].view(np.uint32), ref["times"].view(np.uint32)), what
+        assert np.array_equal(hist[0].astype(np.int64), ref["hist"]), what
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_native_statistics_random_configurations(mcgp, oracle, idx):
+    """Model parity beyond the named cases: random configurations (continuous noise, so exact ties keep measure zero)
+    against the FP64 oracle of the reference, win / podium / position table within 3 sigma (two-stage)."""
+    import random
+    rnd = random.Random(77 + idx)
+    while True:
+        cfg, mc = _random_case(rnd)
+        if cfg["total_laps"] >= 7 and len(mc["grid_probs"]) >= 5:
+            break
+    mc["driver_variance"] = {d: max(v, 0.05) for d, v in mc["driver_variance"].items()}
+    pop = (rnd.choice(["SOFT", "HARD"]), rnd.choice(["MEDIUM", "HARD"]))
+    sim = mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**cfg), pop_no_medium=pop[0], pop_no_soft=pop[1])
+    args = [mc.get(k) for k in MC_KEYS]
+    n_ref = int(4e6 / (cfg["total_laps"] * len(mc["grid_probs"]))) * 10          # ~4 s of oracle time on 8 threads
+    n_ref = max(50000, min(n_ref, 400000))
+    what = f"random {idx}: n={len(mc['grid_probs'])} laps={cfg['total_laps']} {mc['track_condition']} pop={pop}"
+    print(what, assert_agree_two_stage(
+        lambda n, st: sim.run_monte_carlo_counts(n, *args, seed=900 + st, track_condition=mc["track_condition"]),
+        lambda n, st: oracle.run_monte_carlo(cfg, mc, n, 5000 + 10 * st, *pop, threads=8), 10 * n_ref, n_ref, what))
