@@ -252,7 +252,7 @@ def main():
     d2h = N_DRIVERS * N_DRIVERS * 8
 
     # ---- replay mode (BASELINE config 2), reported beside the headline ----------------------------
-    # Throughput only (bit-exactness is tests/ and tools/replay_config2.py): synthetic uniform / normal tapes made
+    # Throughput only (bit-exactness is tests/ and tests/replay_config2.py): synthetic uniform / normal tapes made
     # on the device, cut into per-sim slices of the worst-case draw count (4556 U_py / 1160 Z / 20 U_np).
     replay = None
     if rank == 0:

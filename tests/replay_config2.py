@@ -5,7 +5,7 @@ Chunk c is the reference's run_monte_carlo(n_chunk, ..., seed=42+c) (SURVEY 8(d)
 the unmodified reference on the golden fixtures) produces that chunk's MT19937 / legacy-Gaussian draw tapes and its
 finishing orders / race times; the GPU replays the tapes through the C ABI and every sim is compared.
 
-    python tools/replay_config2.py [--chunks 1000] [--chunk-sims 10000] [--threads 16] [--out profiles/x.json]
+    python tests/replay_config2.py [--chunks 1000] [--chunk-sims 10000] [--threads 16] [--out profiles/x.json]
 This is a checker script (it runs the oracle), not a product path.
 """
 import argparse, json, os, sys, time

@@ -69,11 +69,8 @@ def test_replay_tape_overrun_is_an_error(mcgp, oracle):
 
 
 def test_config2_chunked_replay_is_bit_exact(mcgp, oracle):
-    """BASELINE config 2 at reduced size (the full 10 M sims: tools/replay_config2.py, result in profiles/): chunk c is
+    """BASELINE config 2 at reduced size (the full 10 M sims: tests/replay_config2.py, result in profiles/): chunk c is
     the reference's run_monte_carlo(10 000, seed=42+c); chunk 0 is config 1, whose count table is a golden fixture."""
-    import os
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import replay_config2
     r = replay_config2.run(chunks=12, chunk_sims=10000, threads=8)
     assert r["sims"] == 120000
