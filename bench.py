@@ -34,8 +34,8 @@ sys.path.insert(0, ROOT)
 
 W_RACE = {57: 17100, 78: 23190}  # algorithmic warp-instructions per race, SURVEY.md §8(d)
 # From the committed ncu capture of this kernel build (profiles/, `ncu --set full`, 2 M races, one launch):
-NCU = {"capture": "profiles/r1j_native_kernel_ncu_raw.csv", "executed_warp_instr_per_race": 11065.0,
-       "dram_bytes_per_launch": 40448}
+NCU = {"capture": "profiles/r1m_native_kernel_ncu_raw.csv", "executed_warp_instr_per_race": 11091.3,
+       "dram_bytes_per_launch": 65792}
 N_DRIVERS, LAPS = 20, 57
 WORKLOAD = "bahrain57: 20 drivers x 57 laps, native Philox4x32-10/FP32, synthetic inputs of SURVEY 8(d)"
 
