@@ -18,10 +18,9 @@ struct NativeRace {
     int32_t grid_fixed;   // 1: grid_probs is a deterministic permutation, fixed_slot[] is the grid
     int32_t _pad;
     float pit_loss, drs_delta, dirty_thr, dirty_pen;
-    float ovt32, drs32;                      // overtake_delta and drs_delta x 2^15 (exact): the overtake test runs on x 2^15 paces
+    float drs32;                             // drs_delta x 2^15: the overtake probability runs on x 2^15 paces
+    float _pad2;
     uint32_t red_thr, sc_thr, vsc_thr;       // CUMULATIVE floor(P * 2^32): red if w < red_thr, else SC if w < sc_thr, else VSC if w < vsc_thr
-    float pace32[MCGP_LANES];                // base_pace x 2^15
-    float deg32[MCGP_LANES];                 // raw tire_deg x 2^15 (overtake pace, src/simulation.py:514)
     float sigma[MCGP_LANES];                 // driver_variance
     float dnf_scale[MCGP_LANES];             // 1 / ln(1 - dnf_rate) <= 0: retirement lap = 2 + floor(ln(u) * dnf_scale);
                                              // MCGP_DNF_NEVER for rate <= 0 (laps >= 2, src/simulation.py:190-197)
@@ -31,6 +30,23 @@ struct NativeRace {
     float pc[MCGP_NC][MCGP_LANES];           // base_pace + compound pace delta (:325), rounded to FP32 once
     float grid[MCGP_LANES][MCGP_LANES];      // [pos][driver] qualifying probabilities
     uint8_t fixed_slot[MCGP_LANES];          // grid_fixed: grid slot of each driver
+};
+
+// ---- overtake pace table (native mode) ---------------------------------------------------------
+// The reference decides `pace_delta > overtake_delta` (src/simulation.py:514-521) in FP64 on
+// pace = base_pace + tire_age * tire_deg -- integers times per-driver constants, so with round-number inputs the
+// comparison lands EXACTLY on the threshold for some (driver, age) pairs and FP64 rounding decides it.  FP32
+// arithmetic decides those ties differently (measured: a 3-5 % shift of single position probabilities), so the
+// decision is tabulated on the host in FP64, op for op as upstream: every reachable pace P[d][age] gets its rank
+// `code` among all reachable paces, and every (behind driver, age, DRS) gets the smallest rank `thr` an ahead car's
+// pace must have for fl(fl(P_ahead - P_behind) [+ drs_delta]) > overtake_delta (monotone in P_ahead).  On the GPU
+// the decision is one integer compare, code_ahead >= thr_behind -- bit-identical to the FP64 one.
+// Layout: entry[age][lane], `stride` lanes per row, rows = total_laps + 5 (a tyre set is at most 4 + laps old).
+struct PaceEntry {
+    int32_t code;   // rank of P[d][age] among all reachable paces, 1-based
+    int32_t thr0;   // this car chasing WITHOUT DRS: it may attack iff code_ahead >= thr0
+    int32_t thr1;   // ... with DRS
+    float op32;     // (float)(P[d][age] * 2^15): feeds the overtake PROBABILITY min(0.5, delta / 2) only
 };
 
 // ---- replay mode (FP64, bit-exact) -----------------------------------------------------------

@@ -5,14 +5,17 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/mcgp.h"
 #include "device_params.h"
 
 namespace mcgp {
-cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, unsigned long long n_sims,
+cudaError_t launch_native(const NativeRace* races_dev, const PaceEntry* pace_dev, int pace_rows, int pace_stride, int n_races,
+                          int max_n, unsigned long long n_sims,
                           unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
                           unsigned long long trace_first, unsigned long long trace_count, unsigned long long* work_counter,
@@ -29,6 +32,8 @@ struct mcgp_context {
     int cc_major = 0, cc_minor = 0;
     std::string err;
     NativeRace* native_dev = nullptr;
+    PaceEntry* pace_dev = nullptr;     // [race][pace_rows][pace_stride] overtake pace tables
+    int pace_rows = 0, pace_stride = 0;
     ReplayRace* replay_dev = nullptr;
     unsigned long long* work_counter = nullptr;  // one claim counter per race of the batch (dynamic sim distribution)
     int n_races = 0, n_drivers = 0;
@@ -113,7 +118,7 @@ static void derive_native(const mcgp_race_params* r, NativeRace* o) {
     o->n = n; o->total_laps = r->total_laps; o->track = r->track_condition;
     o->pop_no_medium = r->pop_no_medium; o->pop_no_soft = r->pop_no_soft; o->stream = r->stream;
     o->pit_loss = (float)r->pit_loss; o->drs_delta = (float)r->drs_delta;
-    o->ovt32 = (float)r->overtake_delta * 32768.0f; o->drs32 = (float)r->drs_delta * 32768.0f;
+    o->drs32 = (float)r->drs_delta * 32768.0f;
     o->dirty_thr = (float)r->dirty_air_threshold; o->dirty_pen = (float)r->dirty_air_penalty;
     {   // red flag, else SC, else VSC (:168-176): one draw against the cumulative probabilities
         const double pr = clamp01(r->red_flag_probability), ps = clamp01(r->sc_probability), pv = clamp01(r->vsc_probability);
@@ -125,8 +130,6 @@ static void derive_native(const mcgp_race_params* r, NativeRace* o) {
     }
     for (int d = 0; d < MCGP_LANES; d++) {
         const bool car = d < n;
-        o->pace32[d] = car ? (float)r->base_pace[d] * 32768.0f : 0.0f;
-        o->deg32[d] = car ? (float)r->tire_deg[d] * 32768.0f : 0.0f;
         o->sigma[d] = car ? (float)r->driver_variance[d] : 0.0f;
         o->dnf_scale[d] = car ? dnf_scale(r->dnf_rate[d]) : MCGP_DNF_NEVER;
         o->lap1_thr[d] = car ? prob_threshold(r->team_dnf_rate[d] * 4.0) : 0u;  // LAP_1_DNF_MULTIPLIER :282
@@ -157,6 +160,50 @@ static void derive_native(const mcgp_race_params* r, NativeRace* o) {
         if (fixed) for (int p = 0; p < n; p++) o->fixed_slot[col_owner[p]] = (uint8_t)p;
     }
     o->grid_fixed = fixed ? 1 : 0;
+}
+
+// ---- overtake pace table (device_params.h: PaceEntry) ----------------------------------------
+// FP64, op for op as src/simulation.py:514-521 (this file is compiled with -ffp-contract=off):
+//   pace = base_pace + tire_age * tire_deg;  pace_delta = pace_ahead - pace_behind;  if drs: pace_delta += drs_delta;
+//   eligible = pace_delta > overtake_delta
+static inline bool attack_allowed(double pace_ahead, double pace_behind, bool drs, double drs_delta, double overtake_delta) {
+    volatile double pace_delta = pace_ahead - pace_behind;
+    if (drs) pace_delta = pace_delta + drs_delta;
+    return pace_delta > overtake_delta;
+}
+
+static inline int pace_rows(int total_laps) { return total_laps + 5; }  // tyre age <= 4 (used set at the start) + laps
+
+static void build_pace_table(const mcgp_race_params* r, int rows, int stride, PaceEntry* out) {
+    const int n = r->n_drivers;
+    std::vector<double> P((size_t)rows * n), uniq;
+    for (int a = 0; a < rows; a++)
+        for (int d = 0; d < n; d++) {
+            volatile double wear = (double)a * r->tire_deg[d];
+            P[(size_t)a * n + d] = r->base_pace[d] + wear;
+        }
+    for (double v : P) if (v == v) uniq.push_back(v);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    const int m = (int)uniq.size();
+    for (size_t i = 0; i < (size_t)rows * stride; i++) out[i] = PaceEntry{0, 0x7fffffff, 0x7fffffff, __builtin_nanf("")};
+    for (int a = 0; a < rows; a++)
+        for (int d = 0; d < n; d++) {
+            const double pb = P[(size_t)a * n + d];
+            PaceEntry e{0, 0x7fffffff, 0x7fffffff, (float)(pb * 32768.0)};
+            if (pb == pb) {
+                e.code = 1 + (int)(std::lower_bound(uniq.begin(), uniq.end(), pb) - uniq.begin());
+                for (int k = 0; k < 2; k++) {  // smallest rank an ahead car needs: the decision is monotone in its pace
+                    int lo = 0, hi = m;        // first index in [lo, hi) whose pace is allowed to be attacked; m = none
+                    while (lo < hi) {
+                        const int mid = (lo + hi) / 2;
+                        if (attack_allowed(uniq[mid], pb, k == 1, r->drs_delta, r->overtake_delta)) hi = mid; else lo = mid + 1;
+                    }
+                    (k ? e.thr1 : e.thr0) = lo < m ? lo + 1 : 0x7fffffff;
+                }
+            }
+            out[(size_t)a * stride + d] = e;
+        }
 }
 
 static void derive_replay(const mcgp_race_params* r, ReplayRace* o) {
@@ -211,6 +258,7 @@ int mcgp_destroy(mcgp_handle h) {
     if (!h) return MCGP_OK;
     cudaSetDevice(h->device);
     if (h->native_dev) cudaFree(h->native_dev);
+    if (h->pace_dev) cudaFree(h->pace_dev);
     if (h->replay_dev) cudaFree(h->replay_dev);
     if (h->work_counter) cudaFree(h->work_counter);
     for (int i = 0; i < 8; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
@@ -246,17 +294,32 @@ int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races)
     ReplayRace* rep = new (std::nothrow) ReplayRace[n_races];
     if (!nat || !rep) { delete[] nat; delete[] rep; return fail(h, MCGP_ENOMEM, "out of host memory"); }
     for (int r = 0; r < n_races; r++) { derive_native(&races[r], &nat[r]); derive_replay(&races[r], &rep[r]); }
+    int rows = 0;
+    for (int r = 0; r < n_races; r++) rows = std::max(rows, pace_rows(races[r].total_laps));
+    const int stride = races[0].n_drivers <= 20 ? 20 : MCGP_LANES;
+    const size_t per_race = (size_t)rows * stride;
+    if ((per_race + MCGP_LANES) * sizeof(PaceEntry) > 160u * 1024u) {  // the table is staged in shared memory next to 18 KB of state
+        delete[] nat; delete[] rep;
+        return fail(h, MCGP_EINVAL, "total_laps too large: the overtake pace table (laps + 5 rows) must fit 160 KB of shared memory");
+    }
+    std::vector<PaceEntry> pace;
+    try { pace.resize(per_race * n_races); } catch (...) { delete[] nat; delete[] rep; return fail(h, MCGP_ENOMEM, "out of host memory"); }
+    for (int r = 0; r < n_races; r++) build_pace_table(&races[r], rows, stride, pace.data() + per_race * r);
     if (h->native_dev) { cudaFree(h->native_dev); h->native_dev = nullptr; }
+    if (h->pace_dev) { cudaFree(h->pace_dev); h->pace_dev = nullptr; }
     if (h->replay_dev) { cudaFree(h->replay_dev); h->replay_dev = nullptr; }
     if (h->work_counter) { cudaFree(h->work_counter); h->work_counter = nullptr; }
     cudaError_t e = cudaMalloc(&h->native_dev, sizeof(NativeRace) * n_races);
     if (e == cudaSuccess) e = cudaMalloc(&h->work_counter, sizeof(unsigned long long) * n_races);
     if (e == cudaSuccess) e = cudaMalloc(&h->replay_dev, sizeof(ReplayRace) * n_races);
+    if (e == cudaSuccess) e = cudaMalloc(&h->pace_dev, sizeof(PaceEntry) * pace.size());
     if (e == cudaSuccess) e = cudaMemcpy(h->native_dev, nat, sizeof(NativeRace) * n_races, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->pace_dev, pace.data(), sizeof(PaceEntry) * pace.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->replay_dev, rep, sizeof(ReplayRace) * n_races, cudaMemcpyHostToDevice);
     delete[] nat; delete[] rep;
     if (e != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("upload: ") + cudaGetErrorString(e));
     h->n_races = n_races; h->n_drivers = races[0].n_drivers;
+    h->pace_rows = rows; h->pace_stride = stride;
     return MCGP_OK;
 }
 
@@ -272,7 +335,7 @@ static int launch_native_common(mcgp_handle h, uint64_t n_sims, uint64_t sim_beg
         return fail(h, MCGP_EINVAL, "trace window exceeds the launched sim range");
     CU(cudaSetDevice(h->device));
     static_assert(sizeof(mcgp_trace_record) == sizeof(TraceRecord) && sizeof(TraceRecord) == 8, "trace record layout");
-    CU(mcgp::launch_native(h->native_dev, h->n_races, h->n_drivers, n_sims, sim_begin, seed, (flags & MCGP_F_EXACT_NORMAL) != 0,
+    CU(mcgp::launch_native(h->native_dev, h->pace_dev, h->pace_rows, h->pace_stride, h->n_races, h->n_drivers, n_sims, sim_begin, seed, (flags & MCGP_F_EXACT_NORMAL) != 0,
                            (unsigned long long*)hist_dev, finish_dev, times_dev, (TraceRecord*)(trace_count ? trace_dev : nullptr),
                            trace_first, trace_count, h->work_counter, h->sm_count, (cudaStream_t)cuda_stream));
     h->launches = 2;  // the claim-counter reset + the race kernel

@@ -76,6 +76,12 @@ __device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, fl
     asm volatile("st.volatile.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {  // read-only data: no ordering needed
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
 // index of the highest / lowest set bit (x != 0): FLO, resp. BREV + FLO.SH, without the compiler's 31 - clz detour
 __device__ __forceinline__ int msb(uint32_t x) {
     int r;
@@ -147,7 +153,8 @@ struct NativeOutputs {
 // kOut: 0 = count table only, 1 = + finish/times, 2 = + per-lap trace
 template <int NV4, bool kExact, int kOut>
 __global__ void __launch_bounds__(kThreads, MCGP_MIN_BLOCKS)
-native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_sims, unsigned long long sim_begin,
+native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict__ ptab, const int pt_rows, const int pt_stride,
+                   unsigned long long n_sims, unsigned long long sim_begin,
                    const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
                    const __grid_constant__ NativeOutputs out, unsigned long long* __restrict__ work_counter) {
     constexpr bool kDetail = kOut >= 1, kTrace = kOut >= 2;
@@ -155,6 +162,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     uint8_t* __restrict__ finish = out.finish;
     float* __restrict__ times = out.times;
     __shared__ NativeRace R;
+    extern __shared__ __align__(16) uint4 PT[];  // overtake pace table [age][lane] (device_params.h: PaceEntry) + one row of padding
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     __shared__ __align__(16) float S_t_all[kWarpsPerBlock][32];
     __shared__ float S_w_all[kWarpsPerBlock][48];              // window scratch: times by OLD rank, -inf / +inf pads
@@ -177,6 +185,9 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         uint32_t* dst = reinterpret_cast<uint32_t*>(&R);
         for (int i = threadIdx.x; i < (int)(sizeof(NativeRace) / 4); i += kThreads) dst[i] = src[i];
         for (int i = threadIdx.x; i < MCGP_LANES * MCGP_LANES; i += kThreads) hist_s[i] = 0;
+        const int pt_n = pt_rows * pt_stride;
+        const uint4* psrc = ptab + (size_t)race * pt_n;
+        for (int i = threadIdx.x; i < pt_n + MCGP_LANES; i += kThreads) PT[i] = i < pt_n ? psrc[i] : make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
 
@@ -204,11 +215,15 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
     const float park_t = __fmul_rn(1e30f, (float)(lane + 1));
     const int park = (NV4 == 5 && lane >= 20) ? lane - 20 : 0;
     // overtake paces are carried pre-scaled by 2^15 (exact) so that the 16-bit uniform compares against them directly
-    const float pace32 = R.pace32[lane], deg32 = R.deg32[lane], sigma = R.sigma[lane];
+    const float sigma = R.sigma[lane];
+    // this lane's column of the pace table: entry [age][lane] sits at tb0 + age * rowb (lanes without a car read
+    // a neighbouring entry or the padding row; they are retired from lap 0, so nothing of it is used)
+    const uint32_t tb0 = smem_u32(PT) + 16u * (uint32_t)lane;
+    const uint32_t rowb = 16u * (uint32_t)__shfl_sync(FULL, pt_stride, 0);
     const float dnf_scale = R.dnf_scale[lane];
     const uint32_t lap1_thr = R.lap1_thr[lane];
     const float pit_loss = R.pit_loss, drs_delta = R.drs_delta;
-    const float ovt32 = R.ovt32, drs32_on = R.drs32;
+    const float drs32_on = R.drs32;
     const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
     // cumulative event thresholds (red | SC | VSC share one draw); only the event lane ever sees a non-zero ev_any
     const int ev_lane = kSmall ? 31 : 0;
@@ -310,6 +325,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             t = !is_car ? park_t : dnf_lap == 1 ? -(float)(lane + 1) : lt;
             age = __fadd_rn(age, 1.0f);
         }
+        uint32_t tba = tb0 + (uint32_t)(int)age * rowb;  // shared address of this car's pace-table entry at its current tyre age
 
         int drs_until = 2;  // DRS is off through this lap: laps 1-2 (:551), then through the laps an event disables it
         int rank;
@@ -318,6 +334,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
         float4 prev;           // record of the car one rank ahead (REC[rank - 1]), valid whenever have_rank
         bool have_rank;        // warp-uniform: rank / bit / wa / ra / prev / REC describe the current times
         float drs_f = 0.0f, drs32 = 0.0f;  // drs_delta (and x 2^15) while DRS is enabled for this car, else 0
+        bool drs_on = false;
         float fuel = 0.0f;     // (110 - fuel_load) * 0.03 of the current lap: every runner burns 1.5 kg per lap (:221, Q11)
         const bool traced = kTrace && s >= out.trace_first && s - out.trace_first < out.trace_count;
         int tr_event = 0;
@@ -329,9 +346,9 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             ra = rec_sh + 16u * (uint32_t)r;
         };
         // all-cars rank by counting, then publish the records
-        auto full_rank = [&](float op32) {
+        auto full_rank = [&](float op32, float code_f) {
             set_rank(rank_by_count<NV4>(t, S_t, lane, park));
-            sts_f4<0>(ra, t, op32, last, 0.0f);
+            sts_f4<0>(ra, t, op32, last, code_f);
             prev = lds_f4<-16>(ra);
             have_rank = true;
         };
@@ -366,6 +383,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             if (kTrace) tr_drs = drs_now;
             drs_f = drs_now ? drs_delta : 0.0f;
             drs32 = drs_now ? drs32_on : 0.0f;
+            drs_on = drs_now;
             ahead_last = has_pred ? last_pred : 0.0f;  // (retired cars: 0, never read)
             t = __fadd_rn(t, -tl);  // (+inf stays +inf on lanes without a car)
         };
@@ -392,7 +410,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             }
         };
 
-        full_rank(dnf_lap <= 1 ? kNaN : 0.0f);
+        full_rank(dnf_lap <= 1 ? kNaN : 0.0f, 0.0f);
         update_positions(1, dnf_lap <= 1);
         emit_trace(1, dnf_lap <= 1);
 
@@ -432,6 +450,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                     }
                     drs_until = lap + 1;
                 }
+                tba = tb0 + (uint32_t)(int)age * rowb;
             }
 
             // ---- per-car lap (:186-223) --------------------------------------------------------
@@ -447,6 +466,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             last = (ahead_last > 0.0f && t < dirty_thr) ? held : clean;  // (a retired car's `last` is never read)
             if (!dnf) t = __fadd_rn(t, last);
             age = __fadd_rn(age, 1.0f);  // (retired cars age on: harmless, and one predicate less)
+            tba += rowb;
 
             // ---- _handle_pit_stops (:433-494) ----------------------------------------------
             const bool pit = !dnf && age > opt && rem > 5;
@@ -464,13 +484,20 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                     comp = nc;
                     used |= 1u << comp;
                     age = 0.0f;
+                    tba = tb0;
                     tab.load(comp, eff, opt, pc);
                 }
             }
 
             // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
             // overtake pace (x 2^15); NaN for a retired car blocks both pairs it sits in (Q5)
-            const float op32 = dnf ? kNaN : __fmaf_rn(age, deg32, pace32);
+            // The pair test `pace_delta > overtake_delta` (:514-521) is decided in FP64 on the host for every reachable
+            // (driver, tyre age, DRS) and tabulated as pace ranks (device_params.h: PaceEntry): this car, chasing, may
+            // attack the car ahead iff code_ahead >= thr.  The FP32 paces only feed the (continuous) probability.
+            const uint4 pe = lds_u4(tba);
+            const float op32 = dnf ? kNaN : __uint_as_float(pe.w);
+            const float code_f = __uint_as_float(pe.x);
+            const int thr = drs_on ? (int)pe.z : (int)pe.y;
             const float opb = __fadd_rn(op32, -drs32);  // as the chasing car: DRS helps (:517-518)
             // Re-ordering from a good guess.  `rank` holds an order in which few cars are off by more than two places
             // (last lap's order after the lap times were added: true on 4 laps of 5; a run reversal that leapfrogged a
@@ -482,7 +509,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
                 set_rank(rank + (int)moved);
-                sts_f4<0>(ra, t, op32, last, 0.0f);
+                sts_f4<0>(ra, t, op32, last, code_f);
                 const uint32_t cover = __reduce_or_sync(FULL, bit);
                 prev = lds_f4<-16>(ra);
                 have_rank = cover == FULL && !__any_sync(FULL, !(prev.x < t));
@@ -490,12 +517,14 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             window_place();  // first ordering of the lap
             // one pass; returns true when another pass may follow
             auto one_pass = [&](const uint32_t u16) -> bool {
-                if (!have_rank) full_rank(op32);
+                if (!have_rank) full_rank(op32, code_f);
                 const float delta = __fadd_rn(prev.y, -opb);  // pace_ahead - pace_behind (+ drs_delta), x 2^15
-                // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling)
+                // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling); a retired
+                // car on either side makes delta NaN, the NaN-propagating min keeps it and the compare fails (Q5)
                 uint32_t mine;  // bit if this car overtakes the one ahead: two chained compares and ONE select
-                asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f32 p, %1, %2;\n\tsetp.lt.and.f32 q, %3, %4, p;\n\tselp.u32 %0, %5, 0, q;\n\t}"
-                    : "=r"(mine) : "f"(delta), "f"(ovt32), "f"((float)u16), "f"(fminf(32768.0f, delta)), "r"(bit));
+                asm("{\n\t.reg .pred s, q;\n\t.reg .f32 m;\n\tmin.NaN.f32 m, %1, 0f47000000;\n\tsetp.lt.f32 s, %2, m;\n\t"
+                    "setp.ge.and.s32 q, %3, %4, s;\n\tselp.u32 %0, %5, 0, q;\n\t}"
+                    : "=r"(mine) : "f"(delta), "f"((float)u16), "r"(__float_as_int(prev.w)), "r"(thr), "r"(bit));
                 const uint32_t M = __reduce_or_sync(FULL, mine);
                 if (M == 0u) return false;
                 // closed form of the sequential re-write chain :522-531 over runs of consecutive successes: with j the
@@ -511,7 +540,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
                 // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
                 // Verify the presumed order with one neighbour compare instead of re-counting all ranks.
                 set_rank(j + lsb(above));  // j + e - rank with e = rank + lsb(above) the run end
-                sts_f4<0>(ra, t, op32, last, 0.0f);
+                sts_f4<0>(ra, t, op32, last, code_f);
                 prev = lds_f4<-16>(ra);
                 have_rank = !__any_sync(FULL, !(prev.x < t));
                 if (!have_rank) window_place();  // second chance before counting all ranks
@@ -519,7 +548,7 @@ native_race_kernel(const NativeRace* __restrict__ races, unsigned long long n_si
             };
             if (one_pass(u12 & 0xffffu))
                 if (one_pass(u12 >> 16)) one_pass((lap & 1) ? ext >> 16 : ext & 0xffffu);
-            if (!have_rank) full_rank(op32);
+            if (!have_rank) full_rank(op32, code_f);
             update_positions(lap, dnf);
             emit_trace(lap, dnf);
         };
@@ -596,39 +625,66 @@ __global__ void init_work_counters(unsigned long long* wc, int n_races, unsigned
 }
 
 // ---- host-side launcher ------------------------------------------------------------------------
-template <int NV4, bool kExact>
-static void launch_out(int kout, dim3 grid, dim3 block, cudaStream_t st, const NativeRace* races_dev, unsigned long long n_sims,
-                       unsigned long long sim_begin, const PhiloxKeys& key, unsigned long long* hist, const NativeOutputs& out,
-                       unsigned long long* wc) {
-    if (kout == 0) native_race_kernel<NV4, kExact, 0><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out, wc);
-    else if (kout == 1) native_race_kernel<NV4, kExact, 1><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out, wc);
-    else native_race_kernel<NV4, kExact, 2><<<grid, block, 0, st>>>(races_dev, n_sims, sim_begin, key, hist, out, wc);
+struct LaunchArgs {
+    const NativeRace* races;
+    const uint4* ptab;
+    int pt_rows, pt_stride;
+    unsigned long long n_sims, sim_begin;
+    PhiloxKeys key;
+    unsigned long long* hist;
+    NativeOutputs out;
+    unsigned long long* wc;
+    int n_races, sm_count;
+    size_t dyn_smem;
+    cudaStream_t st;
+};
+
+template <int NV4, bool kExact, int kOut>
+static cudaError_t launch_one(const LaunchArgs& a) {
+    auto kern = native_race_kernel<NV4, kExact, kOut>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.dyn_smem);
+    if (e != cudaSuccess) return e;
+    // persistent-style grid: as many blocks as are resident at once (the register budget allows MCGP_MIN_BLOCKS per SM,
+    // a long race's pace table may allow fewer), split evenly over the races of the batch
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, a.dyn_smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    const long long resident = (long long)a.sm_count * per_sm;
+    long long bpr = resident / a.n_races;  // (never more blocks than fit at once: a waiting block could only start late)
+    const long long need = (long long)((a.n_sims + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    if (bpr > need) bpr = need;
+    if (bpr < 1) bpr = 1;
+    const dim3 grid((unsigned)bpr, a.n_races), block(kThreads);
+    init_work_counters<<<1, 32, 0, a.st>>>(a.wc, a.n_races, (unsigned long long)bpr * kWarpsPerBlock);
+    kern<<<grid, block, a.dyn_smem, a.st>>>(a.races, a.ptab, a.pt_rows, a.pt_stride, a.n_sims, a.sim_begin, a.key, a.hist, a.out, a.wc);
+    return cudaGetLastError();
 }
 
-cudaError_t launch_native(const NativeRace* races_dev, int n_races, int max_n, unsigned long long n_sims,
-                          unsigned long long sim_begin, unsigned long long seed, bool exact,
+template <int NV4, bool kExact>
+static cudaError_t launch_out(int kout, const LaunchArgs& a) {
+    if (kout == 0) return launch_one<NV4, kExact, 0>(a);
+    if (kout == 1) return launch_one<NV4, kExact, 1>(a);
+    return launch_one<NV4, kExact, 2>(a);
+}
+
+cudaError_t launch_native(const NativeRace* races_dev, const PaceEntry* pace_dev, int pace_rows, int pace_stride, int n_races,
+                          int max_n, unsigned long long n_sims, unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
                           unsigned long long trace_first, unsigned long long trace_count, unsigned long long* work_counter,
                           int sm_count, cudaStream_t st) {
+    static_assert(sizeof(PaceEntry) == sizeof(uint4), "pace table entries are staged as 16-byte words");
     const int kout = trace ? 2 : (finish != nullptr || times != nullptr) ? 1 : 0;
-    // persistent-style grid: MCGP_MIN_BLOCKS resident blocks per SM, split evenly over the races of the batch
-    const long long resident = (long long)sm_count * MCGP_MIN_BLOCKS;
-    long long bpr = resident / n_races;  // (never more blocks than fit at once: a waiting block could only start late)
-    const long long need = (long long)((n_sims + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    if (bpr > need) bpr = need;
-    if (bpr < 1) bpr = 1;
-    const dim3 grid((unsigned)bpr, n_races), block(kThreads);
-    const PhiloxKeys key = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
-    const NativeOutputs out{finish, times, trace, trace_first, trace ? trace_count : 0ull};
-    init_work_counters<<<1, 32, 0, st>>>(work_counter, n_races, (unsigned long long)bpr * kWarpsPerBlock);
-    if (max_n <= 20) {
-        if (exact) launch_out<5, true>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out, work_counter);
-        else launch_out<5, false>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out, work_counter);
-    } else {
-        if (exact) launch_out<8, true>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out, work_counter);
-        else launch_out<8, false>(kout, grid, block, st, races_dev, n_sims, sim_begin, key, hist, out, work_counter);
-    }
-    return cudaGetLastError();
+    LaunchArgs a;
+    a.races = races_dev; a.ptab = reinterpret_cast<const uint4*>(pace_dev); a.pt_rows = pace_rows; a.pt_stride = pace_stride;
+    a.n_sims = n_sims; a.sim_begin = sim_begin;
+    a.key = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.hist = hist;
+    a.out = NativeOutputs{finish, times, trace, trace_first, trace ? trace_count : 0ull};
+    a.wc = work_counter; a.n_races = n_races; a.sm_count = sm_count; a.st = st;
+    a.dyn_smem = ((size_t)pace_rows * pace_stride + MCGP_LANES) * sizeof(uint4);  // + one padding row (lanes without a car)
+    if (max_n <= 20) return exact ? launch_out<5, true>(kout, a) : launch_out<5, false>(kout, a);
+    return exact ? launch_out<8, true>(kout, a) : launch_out<8, false>(kout, a);
 }
 
 }  // namespace mcgp

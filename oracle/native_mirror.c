@@ -374,8 +374,16 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
             }
             /* ---- _simulate_overtakes :496-536 ---- */
             float op[N32];
-            /* paces x 2^15 (exact scaling): the 16-bit uniform then compares against delta directly */
-            for (int d = 0; d < n; d++) op[d] = cars[d].dnf ? NAN : fmaf(cars[d].age, R.deg_ovt[d] * 32768.0f, R.pace[d] * 32768.0f);
+            double P64[N32];
+            /* The pair test `pace_delta > overtake_delta` (:514-521) is decided in FP64, op for op as upstream (with
+             * round-number inputs it lands exactly on the threshold for some (driver, age) pairs and rounding decides):
+             * the kernel reads the same decision from a host-built rank table.  The x 2^15 FP32 paces only feed the
+             * (continuous) probability: the 16-bit uniform compares against min(32768, delta) directly. */
+            for (int d = 0; d < n; d++) {
+                const double wear = (double)(int)cars[d].age * p->tire_deg[d];
+                P64[d] = p->base_pace[d] + wear;
+                op[d] = cars[d].dnf ? NAN : (float)(P64[d] * 32768.0);
+            }
             for (int pass = 0; pass < 3; pass++) {
                 int ord[N32], succ[N32 + 1], any = 0;
                 float T[N32];
@@ -388,7 +396,9 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
                     const float delta = op[a] + -opb;
                     const uint32_t u16 = pass == 0 ? (u12[b] & 0xffffu) : pass == 1 ? (u12[b] >> 16) : u3[b];
                     /* u16 * 2^-16 < min(0.5, delta / 2), both sides x 2^16 */
-                    succ[r] = delta > R.ovt_delta * 32768.0f && (float)u16 < fminf(32768.0f, delta);
+                    double pace_delta = P64[a] - P64[b];
+                    if (cars[b].drs) pace_delta = pace_delta + p->drs_delta;
+                    succ[r] = !cars[a].dnf && !cars[b].dnf && pace_delta > p->overtake_delta && (float)u16 < fminf(32768.0f, delta);
                     any |= succ[r];
                 }
                 if (!any) break;

@@ -424,6 +424,25 @@ static void simulate_overtakes(const orc_params* p, car_t* cars, int n, draw_src
     }
 }
 
+/* ---- optional per-lap trace of the FP64 race (debug aid for the statistical parity tests; single-threaded) ---- */
+typedef struct { uint8_t position, compound, tire_age, flags; float gap; } orc_trace_rec;
+static orc_trace_rec* g_trace = NULL;
+static int64_t g_trace_cap = 0, g_trace_sim = 0;
+void orc_debug_trace(void* buf, int64_t cap_sims) { g_trace = (orc_trace_rec*)buf; g_trace_cap = cap_sims; g_trace_sim = 0; }
+static void trace_lap(const orc_params* p, const car_t* cars, int n, int lap) {
+    if (!g_trace || g_trace_sim >= g_trace_cap) return;
+    double lead = 0.0; int have = 0;
+    for (int i = 0; i < n; i++) if (!cars[i].dnf && (!have || cars[i].cum < lead)) { lead = cars[i].cum; have = 1; }
+    for (int i = 0; i < n; i++) {
+        orc_trace_rec* r = &g_trace[((g_trace_sim * p->total_laps) + (lap - 1)) * n + cars[i].drv];
+        r->position = cars[i].dnf ? 0 : (uint8_t)cars[i].position;
+        r->compound = (uint8_t)cars[i].compound;
+        r->tire_age = (uint8_t)cars[i].tire_age;
+        r->flags = (uint8_t)((cars[i].dnf ? 1 : 0) | (cars[i].drs ? 2 : 0));
+        r->gap = (float)(cars[i].cum - lead);
+    }
+}
+
 /* simulate_race, src/simulation.py:147-242 (+ _initialize_cars :244-273, _simulate_lap_1 :275-311) */
 static void simulate_race(const orc_params* p, draw_src* ds, const int* grid, car_t* cars, int* finish) {
     int n = p->n_drivers;
@@ -454,6 +473,7 @@ static void simulate_race(const orc_params* p, draw_src* ds, const int* grid, ca
         c->lap = 1;
     }
     update_positions(cars, n, 1, 1);
+    trace_lap(p, cars, n, 1);
     int drs_disabled_until = 0;
 
     for (int lap = 2; lap <= p->total_laps; lap++) { /* :166 */
@@ -491,7 +511,9 @@ static void simulate_race(const orc_params* p, draw_src* ds, const int* grid, ca
         handle_pit_stops(p, cars, n, lap);
         simulate_overtakes(p, cars, n, ds);
         update_positions(cars, n, lap, lap <= drs_disabled_until);
+        trace_lap(p, cars, n, lap);
     }
+    if (g_trace) g_trace_sim++;
 
     /* final classification :231-242 */
     int idx[ORC_MAX_DRIVERS];

@@ -1,0 +1,180 @@
+#!/usr/bin/env python
+"""BASELINE configs 3, 4 and 5 at their FULL sizes on 1 / 2 / 4 / 8 B200s (checker script: it runs the CPU oracle
+for the statistical gates, which is why it lives under tests/).
+
+    python tests/full_size_configs.py [--out gpurun_out/full_configs_1gpu.json]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tests/full_size_configs.py --out ...
+
+  config 3  Monaco-like 78 laps, high safety-car rate, 1 000 000 000 sims sharded over the ranks by global sim index,
+            ONE int64 all-reduce of the count table.  Gates: the table is identical for every number
+            of GPUs (compare `sha256` across the runs), and win / podium / position cells agree with the reference
+            (its bit-exact C port, >= 1e5 sims) within 3 sigma.
+  config 4  the 24-race synthetic season, 1 000 000 sims per race, all 24 races in ONE launch per rank.
+  config 5  the five prediction points (fp1 / fp2 / fp3 / quali / sprint) x {57-lap race, 19-lap sprint-length race},
+            100 000 000 sims each, plus the per-lap trace of a 2 000 000-sim window of the fp1 race (HBM-writing variant).
+
+Every throughput is device-timed with CUDA events on the launch stream, max over ranks; the all-reduce is inside.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+POP = ("SOFT", "MEDIUM")  # what the reference's available.pop() returned in the fixture-generating process (DESIGN (c))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="")
+    ap.add_argument("--scale", type=float, default=1.0, help="multiply every sim count (smoke runs: 0.001)")
+    ap.add_argument("--ref-sims", type=int, default=400_000)
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    import mcgp_b200 as mcgp
+    from mcgp_b200 import distributed as mdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = mcgp.workloads
+    D = list(wl.DRIVER_TEAMS)
+
+    def params_of(name, stream=0, **opts):
+        cfg, mc = wl.workload(name, **opts)
+        sim = mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**cfg), device=local, pop_no_medium=POP[0],
+                                            pop_no_soft=POP[1])
+        p = sim._params(mc["grid_probs"], mc["base_pace"], mc["tire_deg"], mc["driver_variance"], mc["driver_dnf_rates"],
+                        mc["track_condition"], stream=stream)
+        return p, cfg, mc
+
+    def timed_run(sharded, n_sims, seed):
+        """One sharded run + all-reduce; returns (table as numpy, seconds = max over ranks of the device time)."""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        hist = sharded.run(n_sims, seed)
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return hist.cpu().numpy(), float(ms.item()) * 1e-3
+
+    def sha(h):
+        return hashlib.sha256(np.ascontiguousarray(h.astype(np.int64)).tobytes()).hexdigest()
+
+    def oracle_gate(cfg, mc, hist, n_gpu, seed):
+        """3 sigma gate against the CPU oracle (rank 0 only)."""
+        from oracle import pyoracle as po          # checker only
+        import stats_util as su
+        ref = po.run_monte_carlo(cfg, mc, args.ref_sims, seed, POP[0], POP[1], threads=os.cpu_count() or 1)
+        z = su.compare_tables(hist, n_gpu, ref, args.ref_sims)
+        return dict(ref_sims=args.ref_sims, violations=[list(v) for v in su.violations(z)], **su.summary(z))
+
+    res = {"n_gpus": world, "scale": args.scale, "gpu": torch.cuda.get_device_name(local)}
+    t_all = time.perf_counter()
+
+    # ---- config 3 ----------------------------------------------------------------------------------
+    n3 = int(1_000_000_000 * args.scale)
+    p3, cfg3, mc3 = params_of("monaco_sc")
+    sh3 = mdist.ShardedSimulator([p3], device=local)
+    sh3.run(max(1, n3 // 100), 7)  # warm-up
+    h3, s3 = timed_run(sh3, n3, 42)
+    assert int(h3.sum()) == n3 * 20, "config 3: the count table does not add up"
+    t = mdist.tallies(h3[0])
+    res["config3"] = {"workload": "monaco_sc: 20 drivers x 78 laps, sc 0.05 / vsc 0.03 / red 0.005, native Philox seed 42",
+                      "sims": n3, "seconds": s3, "races_per_s": n3 / s3, "driver_laps_per_s": n3 * 78 * 20 / s3,
+                      "sha256_count_table": sha(h3), "win_counts": {D[i]: int(t["win"][i]) for i in range(3)},
+                      "podium_counts": {D[i]: int(t["podium"][i]) for i in range(3)}}
+    if rank == 0:
+        res["config3"]["vs_reference"] = oracle_gate(cfg3, mc3, h3[0], n3, 4242)
+
+    # ---- config 4 ----------------------------------------------------------------------------------
+    n4 = int(1_000_000 * args.scale) or 1
+    plist = [params_of(f"season:{r}", stream=r)[0] for r in range(wl.N_SEASON_RACES)]
+    laps4 = sum(p.total_laps for p in plist)
+    sh4 = mdist.ShardedSimulator(plist, device=local)
+    sh4.run(max(1, n4 // 100), 7)
+    h4, s4 = timed_run(sh4, n4, 2025)
+    assert h4.shape == (24, 20, 20) and int(h4.sum()) == 24 * 20 * n4
+    res["config4"] = {"workload": "24-race synthetic season in one launch per rank", "sims_per_race": n4, "seconds": s4,
+                      "races_per_s": 24 * n4 / s4, "driver_laps_per_s": n4 * laps4 * 20 / s4, "sha256_count_table": sha(h4)}
+
+    # ---- config 5 ----------------------------------------------------------------------------------
+    n5 = int(100_000_000 * args.scale) or 1
+    res["config5"] = {"sims_each": n5, "points": {}}
+    tot_sims = tot_s = 0.0
+    for laps in (57, 19):
+        for k, point in enumerate(("fp1", "fp2", "fp3", "quali", "sprint")):
+            p5, cfg5, mc5 = params_of(f"point:{point}", total_laps=laps)
+            sh5 = mdist.ShardedSimulator([p5], device=local)
+            sh5.run(max(1, n5 // 100), 7)
+            h5, s5 = timed_run(sh5, n5, 500 + k)
+            assert int(h5.sum()) == n5 * 20
+            e = {"seconds": s5, "races_per_s": n5 / s5, "driver_laps_per_s": n5 * laps * 20 / s5,
+                 "sha256_count_table": sha(h5), "p_win_first_driver": float(h5[0, 0, 0]) / n5}
+            if rank == 0 and point in ("fp1", "quali"):
+                e["vs_reference"] = oracle_gate(cfg5, mc5, h5[0], n5, 900 + k)
+            res["config5"]["points"][f"{point}/{laps}laps"] = e
+            tot_sims += n5
+            tot_s += s5
+    res["config5"]["total_sims"] = int(tot_sims)
+    res["config5"]["races_per_s_overall"] = tot_sims / tot_s
+    # trace window (each rank traces its own window; nothing is exchanged)
+    nt = int(2_000_000 * min(1.0, args.scale * 10)) or 1
+    p5, _, _ = params_of("point:fp1")
+    eng = mcgp.capi.get_engine(local)
+    eng.upload_races([p5])
+    tr = torch.empty(nt * 57 * 20 * 8, dtype=torch.uint8, device=dev)
+    ht = torch.zeros((1, 20, 20), dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    eng.launch_native_traced(nt, rank * nt, 500, ht.data_ptr(), tr.data_ptr(), 0, nt, stream=st)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.launch_native_traced(nt, rank * nt, 500, ht.data_ptr(), tr.data_ptr(), 0, nt, stream=st)
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    st_s = float(ms.item()) * 1e-3
+    rec = tr.view(nt, 57, 20, 8)
+    last_pos = rec[:, 56, :, 0].to(torch.int64)  # running position after the final lap, 0 = retired
+    assert int((last_pos > 0).sum()) + int((rec[:, 56, :, 3] & 1).to(torch.int64).sum()) == nt * 20
+    res["config5"]["trace"] = {"traced_sims_per_gpu": nt, "bytes_per_race": 57 * 20 * 8, "seconds": st_s,
+                               "races_per_s": world * nt / st_s, "hbm_write_gb_per_s_per_gpu": nt * 57 * 20 * 8 / st_s / 1e9}
+    res["wall_seconds"] = time.perf_counter() - t_all
+
+    if rank == 0:
+        line = json.dumps(res)
+        print(line)
+        if args.out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+            with open(args.out, "w") as f:
+                f.write(line + "\n")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
