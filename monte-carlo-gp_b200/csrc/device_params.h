@@ -37,16 +37,18 @@ struct NativeRace {
 // pace = base_pace + tire_age * tire_deg -- integers times per-driver constants, so with round-number inputs the
 // comparison lands EXACTLY on the threshold for some (driver, age) pairs and FP64 rounding decides it.  FP32
 // arithmetic decides those ties differently (measured: a 3-5 % shift of single position probabilities), so the
-// decision is tabulated on the host in FP64, op for op as upstream: every reachable pace P[d][age] gets its rank
-// `code` among all reachable paces, and every (behind driver, age, DRS) gets the smallest rank `thr` an ahead car's
-// pace must have for fl(fl(P_ahead - P_behind) [+ drs_delta]) > overtake_delta (monotone in P_ahead).  On the GPU
-// the decision is one integer compare, code_ahead >= thr_behind -- bit-identical to the FP64 one.
+// decision is tabulated on the host in FP64, op for op as upstream.  All reachable paces P[d][age] are sorted and
+// mapped to a STRICTLY increasing sequence of floats f(P) ~ P * 2^15 (equal after rounding only if two paces are
+// closer than 8e-6 s: then the later one is nudged up by one ulp), and for every (chasing driver, age, DRS) the
+// smallest pace an ahead car must have for fl(fl(P_ahead - P_chasing) [+ drs_delta]) > overtake_delta is stored
+// as its float: the decision is monotone in P_ahead, so on the GPU it is ONE float compare, f(P_ahead) >= thr,
+// bit-identical to the FP64 decision; the same floats feed the (continuous) overtake probability.
 // Layout: entry[age][lane], `stride` lanes per row, rows = total_laps + 5 (a tyre set is at most 4 + laps old).
 struct PaceEntry {
-    int32_t code;   // rank of P[d][age] among all reachable paces, 1-based
-    int32_t thr0;   // this car chasing WITHOUT DRS: it may attack iff code_ahead >= thr0
-    int32_t thr1;   // ... with DRS
-    float op32;     // (float)(P[d][age] * 2^15): feeds the overtake PROBABILITY min(0.5, delta / 2) only
+    float op32;     // f(P[d][age])
+    float thr0;     // this car chasing WITHOUT DRS may attack iff op32_ahead >= thr0 (+inf: never)
+    float thr1;     // ... with DRS
+    uint32_t _pad;
 };
 
 // ---- replay mode (FP64, bit-exact) -----------------------------------------------------------

@@ -174,8 +174,10 @@ static inline bool attack_allowed(double pace_ahead, double pace_behind, bool dr
 
 static inline int pace_rows(int total_laps) { return total_laps + 5; }  // tyre age <= 4 (used set at the start) + laps
 
-static void build_pace_table(const mcgp_race_params* r, int rows, int stride, PaceEntry* out) {
-    const int n = r->n_drivers;
+static void build_pace_table(const mcgp_race_params* r, int rows_total, int stride, PaceEntry* out) {
+    const int n = r->n_drivers, rows = pace_rows(r->total_laps);
+    const float inf = __builtin_inff();
+    for (size_t i = 0; i < (size_t)rows_total * stride; i++) out[i] = PaceEntry{__builtin_nanf(""), inf, inf, 0u};
     std::vector<double> P((size_t)rows * n), uniq;
     for (int a = 0; a < rows; a++)
         for (int d = 0; d < n; d++) {
@@ -186,21 +188,23 @@ static void build_pace_table(const mcgp_race_params* r, int rows, int stride, Pa
     std::sort(uniq.begin(), uniq.end());
     uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
     const int m = (int)uniq.size();
-    for (size_t i = 0; i < (size_t)rows * stride; i++) out[i] = PaceEntry{0, 0x7fffffff, 0x7fffffff, __builtin_nanf("")};
+    std::vector<float> f(m);  // strictly increasing float image of the sorted paces
+    for (int i = 0; i < m; i++) {
+        f[i] = (float)(uniq[i] * 32768.0);
+        if (i > 0 && !(f[i] > f[i - 1])) f[i] = nextafterf(f[i - 1], inf);
+    }
     for (int a = 0; a < rows; a++)
         for (int d = 0; d < n; d++) {
             const double pb = P[(size_t)a * n + d];
-            PaceEntry e{0, 0x7fffffff, 0x7fffffff, (float)(pb * 32768.0)};
-            if (pb == pb) {
-                e.code = 1 + (int)(std::lower_bound(uniq.begin(), uniq.end(), pb) - uniq.begin());
-                for (int k = 0; k < 2; k++) {  // smallest rank an ahead car needs: the decision is monotone in its pace
-                    int lo = 0, hi = m;        // first index in [lo, hi) whose pace is allowed to be attacked; m = none
-                    while (lo < hi) {
-                        const int mid = (lo + hi) / 2;
-                        if (attack_allowed(uniq[mid], pb, k == 1, r->drs_delta, r->overtake_delta)) hi = mid; else lo = mid + 1;
-                    }
-                    (k ? e.thr1 : e.thr0) = lo < m ? lo + 1 : 0x7fffffff;
+            if (pb != pb) continue;
+            PaceEntry e{f[std::lower_bound(uniq.begin(), uniq.end(), pb) - uniq.begin()], inf, inf, 0u};
+            for (int k = 0; k < 2; k++) {  // the slowest ahead car this one may attack: the decision is monotone in its pace
+                int lo = 0, hi = m;
+                while (lo < hi) {
+                    const int mid = (lo + hi) / 2;
+                    if (attack_allowed(uniq[mid], pb, k == 1, r->drs_delta, r->overtake_delta)) hi = mid; else lo = mid + 1;
                 }
+                if (lo < m) (k ? e.thr1 : e.thr0) = f[lo];
             }
             out[(size_t)a * stride + d] = e;
         }

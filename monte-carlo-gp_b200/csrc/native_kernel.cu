@@ -218,16 +218,16 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     const float sigma = R.sigma[lane];
     // this lane's column of the pace table: entry [age][lane] sits at tb0 + age * rowb (lanes without a car read
     // a neighbouring entry or the padding row; they are retired from lap 0, so nothing of it is used)
-    const uint32_t tb0 = smem_u32(PT) + 16u * (uint32_t)lane;
+    uint32_t tb0 = smem_u32(PT) + 16u * (uint32_t)lane;
+    asm volatile("" : "+r"(tb0));  // (kept in a register, like grid_sh)
     const uint32_t rowb = 16u * (uint32_t)__shfl_sync(FULL, pt_stride, 0);
-    const float dnf_scale = R.dnf_scale[lane];
-    const uint32_t lap1_thr = R.lap1_thr[lane];
-    const float pit_loss = R.pit_loss, drs_delta = R.drs_delta;
+    // (values needed once per race or only on rare paths -- retirement law, pit loss, red / SC thresholds -- are read
+    // from the shared parameter block where they are used: the hot loop has no register to spare for them)
+    const float drs_delta = R.drs_delta;
     const float drs32_on = R.drs32;
     const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
     // cumulative event thresholds (red | SC | VSC share one draw); only the event lane ever sees a non-zero ev_any
     const int ev_lane = kSmall ? 31 : 0;
-    const uint32_t red_thr = R.red_thr, sc_thr = R.sc_thr;
     uint32_t ev_any = (!kSmall || lane == ev_lane) ? R.vsc_thr : 0u;
     asm volatile("" : "+r"(ev_any));  // keep it a per-lane register: one compare per lap instead of compare + lane test
     const uint32_t stream = __shfl_sync(FULL, R.stream, 0);
@@ -310,8 +310,9 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             float ln_u;
             if (kExact) ln_u = exact_log(ug);
             else { asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ln_u) : "f"(ug)); ln_u = __fmul_rn(ln_u, 0.6931471805599453f); }
+            const float dnf_scale = R.dnf_scale[lane];
             dnf_lap = 2 + (int)(dnf_scale <= MCGP_DNF_NEVER ? 70000.0f : fminf(__fmul_rn(ln_u, dnf_scale), 70000.0f));
-            if (w.x < lap1_thr) dnf_lap = 1;
+            if (w.x < R.lap1_thr[lane]) dnf_lap = 1;
             if (!is_car) dnf_lap = 0;
             float z1, z2;
             if (kExact) exact_normal2(w.y, w.z, z1, z2); else fast_normal2(w.y, w.z, z1, z2);
@@ -334,7 +335,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
         float4 prev;           // record of the car one rank ahead (REC[rank - 1]), valid whenever have_rank
         bool have_rank;        // warp-uniform: rank / bit / wa / ra / prev / REC describe the current times
         float drs_f = 0.0f, drs32 = 0.0f;  // drs_delta (and x 2^15) while DRS is enabled for this car, else 0
-        bool drs_on = false;
+        uint32_t thr_sel = 0x3210u;        // PRMT selector: the no-DRS (first operand) or the DRS (second operand) threshold
         float fuel = 0.0f;     // (110 - fuel_load) * 0.03 of the current lap: every runner burns 1.5 kg per lap (:221, Q11)
         const bool traced = kTrace && s >= out.trace_first && s - out.trace_first < out.trace_count;
         int tr_event = 0;
@@ -346,9 +347,9 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             ra = rec_sh + 16u * (uint32_t)r;
         };
         // all-cars rank by counting, then publish the records
-        auto full_rank = [&](float op32, float code_f) {
+        auto full_rank = [&](float op32) {
             set_rank(rank_by_count<NV4>(t, S_t, lane, park));
-            sts_f4<0>(ra, t, op32, last, code_f);
+            sts_f4<0>(ra, t, op32, last, 0.0f);
             prev = lds_f4<-16>(ra);
             have_rank = true;
         };
@@ -383,7 +384,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             if (kTrace) tr_drs = drs_now;
             drs_f = drs_now ? drs_delta : 0.0f;
             drs32 = drs_now ? drs32_on : 0.0f;
-            drs_on = drs_now;
+            thr_sel = drs_now ? 0x7654u : 0x3210u;
             ahead_last = has_pred ? last_pred : 0.0f;  // (retired cars: 0, never read)
             t = __fadd_rn(t, -tl);  // (+inf stays +inf on lanes without a car)
         };
@@ -410,7 +411,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             }
         };
 
-        full_rank(dnf_lap <= 1 ? kNaN : 0.0f, 0.0f);
+        full_rank(dnf_lap <= 1 ? kNaN : 0.0f);
         update_positions(1, dnf_lap <= 1);
         emit_trace(1, dnf_lap <= 1);
 
@@ -423,7 +424,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             // ---- race-interrupting events (:168-176): one draw on the cumulative thresholds ---------
             if (__any_sync(FULL, ev < ev_any)) {  // rare (2.7 % of laps with the product probabilities)
                 const uint32_t roll = (lap & 1) ? evz >> 16 : evz & 0xffffu;
-                const int code = ev < red_thr ? 1 : ev < sc_thr ? 2 : (roll < kVscRoll16 ? 4 : 3);
+                const int code = ev < R.red_thr ? 1 : ev < R.sc_thr ? 2 : (roll < kVscRoll16 ? 4 : 3);
                 const int e = __shfl_sync(FULL, code, ev_lane);
                 const bool out_before = lap > dnf_lap;  // retired on an earlier lap (this lap's retirements still run here)
                 const int pos_live = live_position(!out_before);
@@ -473,7 +474,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             if (kTrace) tr_pit = pit;
             if (__any_sync(FULL, pit)) {
                 if (pit) {
-                    t = __fadd_rn(t, pit_loss);
+                    t = __fadd_rn(t, R.pit_loss);
                     int nc = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
                     const uint32_t ud = used & 7u;
                     if (track == 0 && __popc(ud) == 1 && ((ud >> nc) & 1u)) {  // two-compound rule :481-488
@@ -492,12 +493,12 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
             // overtake pace (x 2^15); NaN for a retired car blocks both pairs it sits in (Q5)
             // The pair test `pace_delta > overtake_delta` (:514-521) is decided in FP64 on the host for every reachable
-            // (driver, tyre age, DRS) and tabulated as pace ranks (device_params.h: PaceEntry): this car, chasing, may
-            // attack the car ahead iff code_ahead >= thr.  The FP32 paces only feed the (continuous) probability.
+            // (driver, tyre age, DRS) and tabulated (device_params.h: PaceEntry): this car, chasing, may attack the car
+            // ahead iff op32_ahead >= thr -- one float compare that reproduces the FP64 decision bit for bit.
             const uint4 pe = lds_u4(tba);
-            const float op32 = dnf ? kNaN : __uint_as_float(pe.w);
-            const float code_f = __uint_as_float(pe.x);
-            const int thr = drs_on ? (int)pe.z : (int)pe.y;
+            const float op32 = dnf ? kNaN : __uint_as_float(pe.x);
+            float thr;
+            asm("prmt.b32 %0, %1, %2, %3;" : "=f"(thr) : "r"(pe.y), "r"(pe.z), "r"(thr_sel));
             const float opb = __fadd_rn(op32, -drs32);  // as the chasing car: DRS helps (:517-518)
             // Re-ordering from a good guess.  `rank` holds an order in which few cars are off by more than two places
             // (last lap's order after the lap times were added: true on 4 laps of 5; a run reversal that leapfrogged a
@@ -509,7 +510,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
                 set_rank(rank + (int)moved);
-                sts_f4<0>(ra, t, op32, last, code_f);
+                sts_f4<0>(ra, t, op32, last, 0.0f);
                 const uint32_t cover = __reduce_or_sync(FULL, bit);
                 prev = lds_f4<-16>(ra);
                 have_rank = cover == FULL && !__any_sync(FULL, !(prev.x < t));
@@ -517,14 +518,14 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             window_place();  // first ordering of the lap
             // one pass; returns true when another pass may follow
             auto one_pass = [&](const uint32_t u16) -> bool {
-                if (!have_rank) full_rank(op32, code_f);
+                if (!have_rank) full_rank(op32);
                 const float delta = __fadd_rn(prev.y, -opb);  // pace_ahead - pace_behind (+ drs_delta), x 2^15
                 // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling); a retired
                 // car on either side makes delta NaN, the NaN-propagating min keeps it and the compare fails (Q5)
                 uint32_t mine;  // bit if this car overtakes the one ahead: two chained compares and ONE select
                 asm("{\n\t.reg .pred s, q;\n\t.reg .f32 m;\n\tmin.NaN.f32 m, %1, 0f47000000;\n\tsetp.lt.f32 s, %2, m;\n\t"
-                    "setp.ge.and.s32 q, %3, %4, s;\n\tselp.u32 %0, %5, 0, q;\n\t}"
-                    : "=r"(mine) : "f"(delta), "f"((float)u16), "r"(__float_as_int(prev.w)), "r"(thr), "r"(bit));
+                    "setp.ge.and.f32 q, %3, %4, s;\n\tselp.u32 %0, %5, 0, q;\n\t}"
+                    : "=r"(mine) : "f"(delta), "f"((float)u16), "f"(prev.y), "f"(thr), "r"(bit));
                 const uint32_t M = __reduce_or_sync(FULL, mine);
                 if (M == 0u) return false;
                 // closed form of the sequential re-write chain :522-531 over runs of consecutive successes: with j the
@@ -540,7 +541,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
                 // Verify the presumed order with one neighbour compare instead of re-counting all ranks.
                 set_rank(j + lsb(above));  // j + e - rank with e = rank + lsb(above) the run end
-                sts_f4<0>(ra, t, op32, last, code_f);
+                sts_f4<0>(ra, t, op32, last, 0.0f);
                 prev = lds_f4<-16>(ra);
                 have_rank = !__any_sync(FULL, !(prev.x < t));
                 if (!have_rank) window_place();  // second chance before counting all ranks
@@ -548,7 +549,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             };
             if (one_pass(u12 & 0xffffu))
                 if (one_pass(u12 >> 16)) one_pass((lap & 1) ? ext >> 16 : ext & 0xffffu);
-            if (!have_rank) full_rank(op32, code_f);
+            if (!have_rank) full_rank(op32);
             update_positions(lap, dnf);
             emit_trace(lap, dnf);
         };

@@ -22,6 +22,7 @@
 #include "native_mirror.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 typedef struct { uint32_t x, y, z, w; } u4;
@@ -120,6 +121,47 @@ typedef struct {
     float pit_loss, ovt_delta, drs_delta, dirty_thr, dirty_pen;
     int grid_fixed, fixed_slot[N32];
 } nat_t;
+
+/* Overtake paces for the PROBABILITY (x 2^15, FP32): all reachable paces base_pace + age * tire_deg (FP64, :514-515),
+ * sorted, mapped to a strictly increasing float sequence (two paces that round to the same float: the later one is
+ * nudged up by one ulp) -- the same construction as the kernel's host-built pace table, where the strict
+ * monotonicity is what lets ONE float compare reproduce the FP64 pair decision. */
+static int cmp_double(const void* a, const void* b) {
+    const double x = *(const double*)a, y = *(const double*)b;
+    return x < y ? -1 : x > y;
+}
+static float* build_op32(const orc_params* p) {
+    const int n = p->n_drivers, rows = p->total_laps + 5;
+    double* P = (double*)malloc(sizeof(double) * (size_t)rows * n);
+    double* u = (double*)malloc(sizeof(double) * (size_t)rows * n);
+    float* f = (float*)malloc(sizeof(float) * (size_t)rows * n);
+    float* tab = (float*)malloc(sizeof(float) * (size_t)rows * n);
+    int m = 0;
+    for (int a = 0; a < rows; a++)
+        for (int d = 0; d < n; d++) {
+            const double wear = (double)a * p->tire_deg[d];
+            const double v = p->base_pace[d] + wear;
+            P[(size_t)a * n + d] = v;
+            if (v == v) u[m++] = v;
+        }
+    qsort(u, (size_t)m, sizeof(double), cmp_double);
+    int k = 0;
+    for (int i = 0; i < m; i++) if (i == 0 || u[i] != u[k - 1]) u[k++] = u[i];
+    m = k;
+    for (int i = 0; i < m; i++) {
+        f[i] = (float)(u[i] * 32768.0);
+        if (i > 0 && !(f[i] > f[i - 1])) f[i] = nextafterf(f[i - 1], INFINITY);
+    }
+    for (size_t i = 0; i < (size_t)rows * n; i++) {
+        const double v = P[i];
+        if (v != v) { tab[i] = NAN; continue; }
+        int lo = 0, hi = m;  /* first index with u[idx] >= v */
+        while (lo < hi) { const int mid = (lo + hi) / 2; if (u[mid] < v) lo = mid + 1; else hi = mid; }
+        tab[i] = f[lo];
+    }
+    free(P); free(u); free(f);
+    return tab;
+}
 
 static void derive(const orc_params* p, nat_t* o) {
     memset(o, 0, sizeof(*o));
@@ -225,6 +267,7 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
     if (p->n_drivers < 1 || p->n_drivers > N32) return -1;
     nat_t R;
     derive(p, &R);
+    float* op32_tab = build_op32(p);
     const int n = R.n, L = R.L;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     ncar cars[N32];
@@ -382,7 +425,7 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
             for (int d = 0; d < n; d++) {
                 const double wear = (double)(int)cars[d].age * p->tire_deg[d];
                 P64[d] = p->base_pace[d] + wear;
-                op[d] = cars[d].dnf ? NAN : (float)(P64[d] * 32768.0);
+                op[d] = cars[d].dnf ? NAN : op32_tab[(size_t)(int)cars[d].age * n + d];
             }
             for (int pass = 0; pass < 3; pass++) {
                 int ord[N32], succ[N32 + 1], any = 0;
@@ -435,5 +478,6 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
             if (times) times[s * n + d] = c->t;
         }
     }
+    free(op32_tab);
     return 0;
 }
