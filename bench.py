@@ -34,8 +34,8 @@ sys.path.insert(0, ROOT)
 
 W_RACE = {57: 17100, 78: 23190}  # algorithmic warp-instructions per race, SURVEY.md §8(d)
 # From the committed ncu capture of this kernel build (profiles/, `ncu --set full`, 2 M races, one launch):
-NCU = {"capture": "profiles/r1m_native_kernel_ncu_raw.csv", "executed_warp_instr_per_race": 11091.3,
-       "dram_bytes_per_launch": 65792}
+NCU = {"capture": "profiles/r1q_native_kernel_ncu_raw.csv", "executed_warp_instr_per_race": 11332.4,
+       "dram_bytes_per_launch": 212992}
 N_DRIVERS, LAPS = 20, 57
 WORKLOAD = "bahrain57: 20 drivers x 57 laps, native Philox4x32-10/FP32, synthetic inputs of SURVEY 8(d)"
 
@@ -247,8 +247,9 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = S * n_gpus * e2e_steps / float(e2e_t.item())
-    import ctypes
-    h2d = ctypes.sizeof(mcgp.capi.McgpRaceParams) + N_DRIVERS * N_DRIVERS * 8   # params block (+ derived blocks of similar size) and the += table
+    # bytes per step: the += count table both ways, plus what the library uploads on every host-buffer call (the
+    # derived parameter blocks and the overtake pace table, counted by the library itself)
+    h2d = N_DRIVERS * N_DRIVERS * 8 + mcgp.capi.get_engine(local).last_upload_bytes()
     d2h = N_DRIVERS * N_DRIVERS * 8
 
     # ---- replay mode (BASELINE config 2), reported beside the headline ----------------------------
@@ -362,7 +363,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sims_per_gpu_per_step": S, "n_drivers": N_DRIVERS, "laps": LAPS, "seed": seed,
                        "parallelism": f"sim-sharded x{n_gpus}, one int64 all-reduce of the 20x20 count table per step",
-                       "l2": "256 MiB fill between timed steps (outside the per-step events); the kernel's inputs are a 6.6 KB parameter block"},
+                       "l2": "256 MiB fill between timed steps (outside the per-step events); the kernel's inputs are a 6.9 KB parameter block + a 19.8 KB pace table"},
             "driver_laps_per_s": value * N_DRIVERS * LAPS,
             "e2e": {"value": e2e_value, "unit": "races/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "RaceSimulator.run_monte_carlo_counts (host dicts in, count table out)", "steps": e2e_steps},

@@ -127,6 +127,9 @@ int mcgp_run_native_traced(mcgp_handle h, const mcgp_race_params* races, int n_r
                            mcgp_trace_record* trace_host, uint64_t trace_first, uint64_t trace_count);
 /* Number of kernel launches the last mcgp_launch_native / mcgp_run_* call on this handle made. */
 int mcgp_last_launch_count(mcgp_handle h);
+/* Bytes the last mcgp_upload_races on this handle copied host -> device (the derived parameter blocks and the
+ * overtake pace tables of all races); the host-buffer calls upload on every call. */
+uint64_t mcgp_last_upload_bytes(mcgp_handle h);
 
 /* replay mode: FP64, consumes the reference's own draws, bit-exact ------------------------------ *
  * Sim s reads u_py[off[3s]..off[3s+3]) (random.random() values, :168-194,:287,:392,:524),

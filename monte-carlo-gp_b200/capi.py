@@ -61,6 +61,7 @@ _SIGNATURES = {
     "mcgp_last_error": (C.c_char_p, [C.c_void_p]),
     "mcgp_device_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4),
     "mcgp_last_launch_count": (C.c_int, [C.c_void_p]),
+    "mcgp_last_upload_bytes": (C.c_uint64, [C.c_void_p]),
     "mcgp_upload_races": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int]),
     "mcgp_run_native": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int, C.c_uint64, C.c_uint64,
                                   C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -134,6 +135,9 @@ class Engine:
     @property
     def last_launch_count(self) -> int:
         return self._lib.mcgp_last_launch_count(self._h)
+
+    def last_upload_bytes(self) -> int:
+        return int(self._lib.mcgp_last_upload_bytes(self._h))
 
     @staticmethod
     def _pack(races) -> tuple:

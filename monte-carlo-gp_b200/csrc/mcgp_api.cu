@@ -38,6 +38,7 @@ struct mcgp_context {
     unsigned long long* work_counter = nullptr;  // one claim counter per race of the batch (dynamic sim distribution)
     int n_races = 0, n_drivers = 0;
     int launches = 0;
+    uint64_t upload_bytes = 0;
     // grow-only scratch for the host-buffer entry points
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_sz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -284,6 +285,7 @@ int mcgp_device_info(mcgp_handle h, int* sm_count, int* sm_clock_khz, int* cc_ma
 }
 
 int mcgp_last_launch_count(mcgp_handle h) { return h ? h->launches : 0; }
+uint64_t mcgp_last_upload_bytes(mcgp_handle h) { return h ? h->upload_bytes : 0; }
 
 int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races) {
     if (!h) return MCGP_EINVAL;
@@ -324,6 +326,7 @@ int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races)
     if (e != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("upload: ") + cudaGetErrorString(e));
     h->n_races = n_races; h->n_drivers = races[0].n_drivers;
     h->pace_rows = rows; h->pace_stride = stride;
+    h->upload_bytes = (sizeof(NativeRace) + sizeof(ReplayRace)) * (uint64_t)n_races + sizeof(PaceEntry) * (uint64_t)pace.size();
     return MCGP_OK;
 }
 
