@@ -34,6 +34,8 @@ struct mcgp_context {
     NativeRace* native_dev = nullptr;
     PaceEntry* pace_dev = nullptr;     // [race][pace_rows][pace_stride] overtake pace tables
     int pace_rows = 0, pace_stride = 0;
+    int cap_races = 0;                 // allocated capacity of native_dev / replay_dev / work_counter (races)
+    size_t cap_pace = 0;               // allocated capacity of pace_dev (entries)
     ReplayRace* replay_dev = nullptr;
     unsigned long long* work_counter = nullptr;  // one claim counter per race of the batch (dynamic sim distribution)
     int n_races = 0, n_drivers = 0;
@@ -311,14 +313,24 @@ int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races)
     std::vector<PaceEntry> pace;
     try { pace.resize(per_race * n_races); } catch (...) { delete[] nat; delete[] rep; return fail(h, MCGP_ENOMEM, "out of host memory"); }
     for (int r = 0; r < n_races; r++) build_pace_table(&races[r], rows, stride, pace.data() + per_race * r);
-    if (h->native_dev) { cudaFree(h->native_dev); h->native_dev = nullptr; }
-    if (h->pace_dev) { cudaFree(h->pace_dev); h->pace_dev = nullptr; }
-    if (h->replay_dev) { cudaFree(h->replay_dev); h->replay_dev = nullptr; }
-    if (h->work_counter) { cudaFree(h->work_counter); h->work_counter = nullptr; }
-    cudaError_t e = cudaMalloc(&h->native_dev, sizeof(NativeRace) * n_races);
-    if (e == cudaSuccess) e = cudaMalloc(&h->work_counter, sizeof(unsigned long long) * n_races);
-    if (e == cudaSuccess) e = cudaMalloc(&h->replay_dev, sizeof(ReplayRace) * n_races);
-    if (e == cudaSuccess) e = cudaMalloc(&h->pace_dev, sizeof(PaceEntry) * pace.size());
+    // device blocks are grow-only: a product-sized call (10 000 sims = 0.13 ms of kernel) must not pay for cudaMalloc / cudaFree
+    cudaError_t e = cudaSuccess;
+    if (n_races > h->cap_races) {
+        if (h->native_dev) { cudaFree(h->native_dev); h->native_dev = nullptr; }
+        if (h->replay_dev) { cudaFree(h->replay_dev); h->replay_dev = nullptr; }
+        if (h->work_counter) { cudaFree(h->work_counter); h->work_counter = nullptr; }
+        h->cap_races = 0;
+        e = cudaMalloc(&h->native_dev, sizeof(NativeRace) * n_races);
+        if (e == cudaSuccess) e = cudaMalloc(&h->work_counter, sizeof(unsigned long long) * n_races);
+        if (e == cudaSuccess) e = cudaMalloc(&h->replay_dev, sizeof(ReplayRace) * n_races);
+        if (e == cudaSuccess) h->cap_races = n_races;
+    }
+    if (e == cudaSuccess && pace.size() > h->cap_pace) {
+        if (h->pace_dev) { cudaFree(h->pace_dev); h->pace_dev = nullptr; }
+        h->cap_pace = 0;
+        e = cudaMalloc(&h->pace_dev, sizeof(PaceEntry) * pace.size());
+        if (e == cudaSuccess) h->cap_pace = pace.size();
+    }
     if (e == cudaSuccess) e = cudaMemcpy(h->native_dev, nat, sizeof(NativeRace) * n_races, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->pace_dev, pace.data(), sizeof(PaceEntry) * pace.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->replay_dev, rep, sizeof(ReplayRace) * n_races, cudaMemcpyHostToDevice);

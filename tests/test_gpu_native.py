@@ -100,6 +100,27 @@ def test_fast_and_exact_normals_agree_statistically(mcgp):
                                  3000000, 3000000, "fast vs exact normals"))
 
 
+def test_product_sized_calls_and_lap_limit(mcgp, oracle):
+    """The reference's product call is 10 000 sims (src/predictor.py:284): repeated host-buffer calls reuse the device
+    blocks (grow-only) and keep giving the same table; a race too long for the shared-memory pace table is refused
+    with the library's error, not launched."""
+    cfg, mc, seed, _ = gc.get_case("bahrain_dry")
+    sim = _sim(mcgp, cfg)
+    args = [mc.get(k) for k in MC_KEYS]
+    first = sim.run_monte_carlo_counts(10000, *args, seed=42)
+    for _ in range(20):
+        assert np.array_equal(sim.run_monte_carlo_counts(10000, *args, seed=42), first)
+    long_cfg = dict(cfg, total_laps=5000)
+    with pytest.raises(mcgp.capi.McgpError) as e:
+        _sim(mcgp, long_cfg).run_monte_carlo_counts(100, *args, seed=1)
+    assert "pace table" in str(e.value)
+    # afterwards the engine still works (and a longer race than before re-grows the table)
+    cfg78, mc78, _, _ = gc.get_case("monaco_sc")
+    got = _sim(mcgp, cfg78).run_monte_carlo_counts(5000, *[mc78.get(k) for k in MC_KEYS], seed=3)
+    assert int(got.sum()) == 5000 * 20
+    assert np.array_equal(sim.run_monte_carlo_counts(10000, *args, seed=42), first)
+
+
 def test_sim_range_split_invariance(mcgp):
     """Counter-based RNG keyed by the global sim index: [0,N) == [0,a) + [a,b) + [b,N) (the multi-GPU sharding)."""
     cfg, mc, seed, _ = gc.get_case("events")
