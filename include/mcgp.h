@@ -130,6 +130,14 @@ int mcgp_last_launch_count(mcgp_handle h);
 /* Bytes the last mcgp_upload_races on this handle copied host -> device (the derived parameter blocks and the
  * overtake pace tables of all races); the host-buffer calls upload on every call. */
 uint64_t mcgp_last_upload_bytes(mcgp_handle h);
+/* Host-only (no device, no handle): the overtake pace table mcgp_upload_races derives for one race, so that a
+ * binding can inspect or test it.  The reference decides `pace_delta > overtake_delta` (src/simulation.py:514-521)
+ * in FP64 on pace = base_pace + tire_age * tire_deg; the table holds, per tyre age a (rows) and driver d (`stride`
+ * entries per row), four floats {f(P[d][a]), thr_no_drs, thr_drs, 0}: driver b on tyres of age A_b, chasing driver a
+ * on tyres of age A_a, may attack iff  f(P[a][A_a]) >= thr[b][A_b]  -- by construction the same truth value as
+ * fl(fl(P_a - P_b) [+ drs_delta]) > overtake_delta.  out == NULL: only the sizes are returned.
+ * out must hold rows * stride * 4 floats. */
+int mcgp_pace_table(const mcgp_race_params* race, int32_t* rows, int32_t* stride, float* out);
 
 /* replay mode: FP64, consumes the reference's own draws, bit-exact ------------------------------ *
  * Sim s reads u_py[off[3s]..off[3s+3]) (random.random() values, :168-194,:287,:392,:524),

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "mcgp_device_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4),
     "mcgp_last_launch_count": (C.c_int, [C.c_void_p]),
     "mcgp_last_upload_bytes": (C.c_uint64, [C.c_void_p]),
+    "mcgp_pace_table": (C.c_int, [C.POINTER(McgpRaceParams), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
     "mcgp_upload_races": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int]),
     "mcgp_run_native": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int, C.c_uint64, C.c_uint64,
                                   C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -219,6 +220,21 @@ class Engine:
 
 
 _engines: dict[int, Engine] = {}
+
+
+def pace_table(race: McgpRaceParams) -> np.ndarray:
+    """The overtake pace table the library derives for one race (host-only, needs no GPU): float32
+    [rows = laps + 5, stride, 4] with entries {f(P[d][age]), thr_no_drs, thr_drs, 0} (include/mcgp.h: mcgp_pace_table)."""
+    lib = load_library()
+    rows, stride = C.c_int32(0), C.c_int32(0)
+    rc = lib.mcgp_pace_table(C.byref(race), C.byref(rows), C.byref(stride), None)
+    if rc:
+        raise McgpError(rc, "mcgp_pace_table: invalid race parameters")
+    out = np.zeros((rows.value, stride.value, 4), np.float32)
+    rc = lib.mcgp_pace_table(C.byref(race), C.byref(rows), C.byref(stride), _p(out))
+    if rc:
+        raise McgpError(rc, "mcgp_pace_table failed")
+    return out
 
 
 def get_engine(device: int = 0) -> Engine:

@@ -289,6 +289,18 @@ int mcgp_device_info(mcgp_handle h, int* sm_count, int* sm_clock_khz, int* cc_ma
 int mcgp_last_launch_count(mcgp_handle h) { return h ? h->launches : 0; }
 uint64_t mcgp_last_upload_bytes(mcgp_handle h) { return h ? h->upload_bytes : 0; }
 
+int mcgp_pace_table(const mcgp_race_params* race, int32_t* rows, int32_t* stride, float* out) {
+    if (!race || race->n_drivers < 1 || race->n_drivers > MCGP_MAX_DRIVERS || race->total_laps < 1) return MCGP_EINVAL;
+    const int r = pace_rows(race->total_laps), st = race->n_drivers <= 20 ? 20 : MCGP_LANES;
+    if (rows) *rows = r;
+    if (stride) *stride = st;
+    if (out) {
+        static_assert(sizeof(PaceEntry) == 4 * sizeof(float), "PaceEntry is four 32-bit words");
+        build_pace_table(race, r, st, reinterpret_cast<PaceEntry*>(out));
+    }
+    return MCGP_OK;
+}
+
 int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races) {
     if (!h) return MCGP_EINVAL;
     if (!races || n_races < 1) return fail(h, MCGP_EINVAL, "races is NULL or n_races < 1");
