@@ -34,8 +34,11 @@ sys.path.insert(0, ROOT)
 
 W_RACE = {57: 17100, 78: 23190}  # algorithmic warp-instructions per race, SURVEY.md §8(d)
 # From the committed ncu capture of this kernel build (profiles/, `ncu --set full`, 2 M races, one launch):
-NCU = {"capture": "profiles/r1q_native_kernel_ncu_raw.csv", "executed_warp_instr_per_race": 11332.4,
-       "dram_bytes_per_launch": 212992}
+NCU = {"capture": "profiles/r1s_native_kernel_ncu_raw.csv", "executed_warp_instr_per_race": 10865.9,
+       # dram__bytes_read.sum + dram__bytes_write.sum of that launch: 13.6 MB + 48.0 MB, i.e. write-back of the 256 MiB
+       # L2-flush fill that precedes it; the kernel's own input is 27 KB per block out of L2 (captures whose launch
+       # is not preceded by a fill show 0.06-0.2 MB: profiles/r1m, r1q)
+       "dram_bytes_per_launch": 61560576}
 N_DRIVERS, LAPS = 20, 57
 WORKLOAD = "bahrain57: 20 drivers x 57 laps, native Philox4x32-10/FP32, synthetic inputs of SURVEY 8(d)"
 
@@ -378,7 +381,7 @@ def main():
                          "note": "no dense contraction and ~0 HBM traffic (SURVEY 8(d)): the bound is warp-instruction issue, "
                                  "N_SM x 4 x f_SM.  frac = ALGORITHMIC work (17 100 warp-instr per race, SURVEY 8(d)) / peak; "
                                  "issue_slot_utilisation = instructions this kernel actually executes (ncu, "
-                                 + NCU["capture"] + ") x races/s / peak; traffic = dram bytes read+written per launch (ncu)"},
+                                 + NCU["capture"] + ") x races/s / peak; traffic = dram bytes read+written during that launch (ncu): write-back of the preceding 256 MiB L2-flush fill, the kernel's own input is 27 KB per block"},
             "cpu_baseline": cpu,
             "replay_mode": replay,
             "season_batch": aux.get("season_batch"), "trace_mode": aux.get("trace_mode"),
