@@ -20,6 +20,12 @@
 //     time re-write chain of :522-531 collapses to a closed form over runs of consecutive successes
 //     (one REDUX.OR + bit scans), and the order after a pass is the old one with each run reversed
 //     (verified with one neighbour compare);
+//   * the one comparison of the loop whose operands carry no noise, `pace_delta > overtake_delta` (:514-521), is the
+//     reference's FP64 decision bit for bit: the host tabulates it per (driver, tyre age, DRS) as strictly increasing
+//     float images of the FP64 paces (device_params.h: PaceEntry), staged in shared memory; one LDS.128 per lap and one
+//     float compare per pair (FP32 paces decided exact ties of the round-number BASELINE inputs differently);
+//   * the lap loop is unrolled by PAIRS (the unit of the draw schedule), so which half of a pair's draws a lap uses is
+//     a compile-time fact;
 //   * the finish-position histogram accumulates in shared memory (uint32) and is flushed once per
 //     block with 64-bit global atomics.
 // The scalar CPU mirror of exactly this algorithm is oracle/native_mirror.c (test infrastructure).
