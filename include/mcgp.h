@@ -53,7 +53,8 @@ enum {
  * (x4 lap-1 multiplier, 0.85/1.1 stint scaling, deg/0.05 driver factor) itself. */
 typedef struct mcgp_race_params {
     int32_t n_drivers;       /* 1..MCGP_MAX_DRIVERS                                              */
-    int32_t total_laps;      /* RaceConfig.total_laps, 1..65535                                   */
+    int32_t total_laps;      /* RaceConfig.total_laps, 1..505 (n_drivers <= 20) / 1..314 (more):   *
+                              * the per-race overtake pace table must fit in shared memory      */
     int32_t track_condition; /* MCGP_DRY / MCGP_DAMP / MCGP_WETTRACK                              */
     int32_t pop_no_medium;   /* `({S,M,H}-{M}).pop()`: MCGP_SOFT or MCGP_HARD  (src/simulation.py:486)  */
     int32_t pop_no_soft;     /* `({S,M,H}-{S}).pop()`: MCGP_MEDIUM or MCGP_HARD (src/simulation.py:488) */

@@ -93,7 +93,7 @@ static double clamp01(double p) { return !(p > 0.0) ? 0.0 : p > 1.0 ? 1.0 : p; }
 
 static int validate(mcgp_handle h, const mcgp_race_params* r) {
     if (r->n_drivers < 1 || r->n_drivers > MCGP_MAX_DRIVERS) return fail(h, MCGP_EINVAL, "n_drivers must be in 1..32");
-    if (r->total_laps < 1 || r->total_laps > 65535) return fail(h, MCGP_EINVAL, "total_laps must be in 1..65535");
+    if (r->total_laps < 1 || r->total_laps > 65535) return fail(h, MCGP_EINVAL, "total_laps must be positive (and small enough for the pace table: 505 laps for <= 20 drivers, 314 for more)");
     if (r->track_condition < 0 || r->track_condition > 2) return fail(h, MCGP_EINVAL, "bad track_condition");
     if (!(r->pop_no_medium == MCGP_SOFT || r->pop_no_medium == MCGP_HARD)) return fail(h, MCGP_EINVAL, "pop_no_medium must be SOFT or HARD");
     if (!(r->pop_no_soft == MCGP_MEDIUM || r->pop_no_soft == MCGP_HARD)) return fail(h, MCGP_EINVAL, "pop_no_soft must be MEDIUM or HARD");
@@ -292,6 +292,7 @@ uint64_t mcgp_last_upload_bytes(mcgp_handle h) { return h ? h->upload_bytes : 0;
 int mcgp_pace_table(const mcgp_race_params* race, int32_t* rows, int32_t* stride, float* out) {
     if (!race || race->n_drivers < 1 || race->n_drivers > MCGP_MAX_DRIVERS || race->total_laps < 1) return MCGP_EINVAL;
     const int r = pace_rows(race->total_laps), st = race->n_drivers <= 20 ? 20 : MCGP_LANES;
+    if (((size_t)r * st + MCGP_LANES) * sizeof(PaceEntry) > 160u * 1024u) return MCGP_EINVAL;  // same limit as mcgp_upload_races
     if (rows) *rows = r;
     if (stride) *stride = st;
     if (out) {
