@@ -336,6 +336,11 @@ def main():
             aux["trace_mode"] = {"sims": n5, "races_per_s": n5 / (ms * 1e-3), "trace_bytes_per_race": LAPS * N_DRIVERS * 8,
                                  "hbm_write_gb_per_s": n5 * LAPS * N_DRIVERS * 8 / (ms * 1e-3) / 1e9, "ms": ms}
             del tr
+            # config 5's alternative output: the trace reduced on-chip to per-lap position histograms (57 x 20 x 20 counters)
+            lh = torch.zeros((1, LAPS, N_DRIVERS, N_DRIVERS), dtype=torch.int64, device=dev)
+            h6 = torch.zeros((1, N_DRIVERS, N_DRIVERS), dtype=torch.int64, device=dev)
+            ms = timed(lambda: eng.launch_native_laphist(S, 0, seed, h6.data_ptr(), lh.data_ptr(), stream=st))
+            aux["lap_histogram_mode"] = {"sims": S, "races_per_s": S / (ms * 1e-3), "counters": LAPS * N_DRIVERS * N_DRIVERS, "ms": ms}
             eng.upload_races([params])
         except Exception as e:  # auxiliary figures; never lose the headline line over them
             aux["error"] = repr(e)
@@ -385,6 +390,7 @@ def main():
             "cpu_baseline": cpu,
             "replay_mode": replay,
             "season_batch": aux.get("season_batch"), "trace_mode": aux.get("trace_mode"),
+            "lap_histogram_mode": aux.get("lap_histogram_mode"),
         }
         if "error" in aux:
             line["aux_error"] = aux["error"]

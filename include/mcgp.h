@@ -126,6 +126,17 @@ int mcgp_launch_native_traced(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin
 int mcgp_run_native_traced(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims,
                            uint64_t sim_begin, uint64_t seed, uint32_t flags, uint64_t* hist_host,
                            mcgp_trace_record* trace_host, uint64_t trace_first, uint64_t trace_count);
+/* Per-lap position histogram (the on-chip reduction of the trace; absent upstream): besides hist, the launch
+ * accumulates (+=)  laphist[((r * laps + lap-1) * n + driver) * n + pos]  = number of sims in which `driver` RUNS in
+ * position pos (0 = leading) after lap `lap`; retired cars are not counted, so a row sums to the number of sims in
+ * which the driver is still running.  laps = mcgp_lap_histogram_laps(h) = the longest race of the uploaded batch.
+ * laps * n * n * 4 B + the pace table must fit 180 KB of shared memory (57 laps x 20 cars: 111 KB). */
+int mcgp_lap_histogram_laps(mcgp_handle h);
+int mcgp_launch_native_laphist(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
+                               uint64_t* hist_dev, uint64_t* laphist_dev, void* cuda_stream);
+int mcgp_run_native_laphist(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims,
+                            uint64_t sim_begin, uint64_t seed, uint32_t flags, uint64_t* hist_host,
+                            uint64_t* laphist_host);
 /* Number of kernel launches the last mcgp_launch_native / mcgp_run_* call on this handle made. */
 int mcgp_last_launch_count(mcgp_handle h);
 /* Bytes the last mcgp_upload_races on this handle copied host -> device (the derived parameter blocks and the

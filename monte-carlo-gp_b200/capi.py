@@ -72,6 +72,11 @@ _SIGNATURES = {
                                             C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mcgp_run_native_traced": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int, C.c_uint64, C.c_uint64,
                                          C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "mcgp_lap_histogram_laps": (C.c_int, [C.c_void_p]),
+    "mcgp_launch_native_laphist": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]),
+    "mcgp_run_native_laphist": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int, C.c_uint64, C.c_uint64,
+                                          C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "mcgp_run_replay": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_uint64] + [C.c_void_p] * 10),
     "mcgp_launch_replay": (C.c_int, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 12),
 }
@@ -177,6 +182,24 @@ class Engine:
                                                      _p(hist), _p(trace), trace_first, trace_count))
         self.n_races, self.n_drivers = n_races, n
         return hist, trace
+
+    def run_native_laphist(self, races, n_sims: int, sim_begin: int = 0, seed: int = 0, flags: int = 0):
+        """Host-buffer call that also returns the per-lap position histogram: (hist [n_races, n, n],
+        laphist [n_races, laps, n, n]) with laphist[r, lap-1, d, pos] = sims in which driver d RUNS in position pos
+        (0 = leading) after lap `lap`; laps = the longest race of the batch (include/mcgp.h: mcgp_run_native_laphist)."""
+        arr, n_races, n = self._pack(races)
+        laps = max(r.total_laps for r in races)
+        hist = np.zeros((n_races, n, n), np.uint64)
+        laphist = np.zeros((n_races, laps, n, n), np.uint64)
+        self._check(self._lib.mcgp_run_native_laphist(self._h, arr, n_races, n_sims, sim_begin, seed & (2 ** 64 - 1), flags,
+                                                      _p(hist), _p(laphist)))
+        self.n_races, self.n_drivers = n_races, n
+        assert self._lib.mcgp_lap_histogram_laps(self._h) == laps
+        return hist, laphist
+
+    def launch_native_laphist(self, n_sims, sim_begin, seed, hist_ptr, laphist_ptr, flags=0, stream=None):
+        self._check(self._lib.mcgp_launch_native_laphist(self._h, n_sims, sim_begin, seed & (2 ** 64 - 1), flags, _p(hist_ptr),
+                                                         _p(laphist_ptr), _p(stream)))
 
     def launch_native_traced(self, n_sims, sim_begin, seed, hist_ptr, trace_ptr, trace_first, trace_count, flags=0,
                              stream=None):

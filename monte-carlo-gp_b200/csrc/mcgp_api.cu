@@ -18,8 +18,8 @@ cudaError_t launch_native(const NativeRace* races_dev, const PaceEntry* pace_dev
                           int max_n, unsigned long long n_sims,
                           unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
-                          unsigned long long trace_first, unsigned long long trace_count, unsigned long long* work_counter,
-                          int sm_count, cudaStream_t st);
+                          unsigned long long trace_first, unsigned long long trace_count, unsigned long long* laphist,
+                          unsigned long long* work_counter, int sm_count, cudaStream_t st);
 cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
@@ -357,7 +357,7 @@ int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races)
 
 static int launch_native_common(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
                                 uint64_t* hist_dev, uint8_t* finish_dev, float* times_dev, mcgp_trace_record* trace_dev,
-                                uint64_t trace_first, uint64_t trace_count, void* cuda_stream) {
+                                uint64_t trace_first, uint64_t trace_count, void* cuda_stream, uint64_t* laphist_dev = nullptr) {
     if (!h) return MCGP_EINVAL;
     if (!h->native_dev) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
     if (!hist_dev) return fail(h, MCGP_EINVAL, "hist_dev is NULL");
@@ -369,7 +369,8 @@ static int launch_native_common(mcgp_handle h, uint64_t n_sims, uint64_t sim_beg
     static_assert(sizeof(mcgp_trace_record) == sizeof(TraceRecord) && sizeof(TraceRecord) == 8, "trace record layout");
     CU(mcgp::launch_native(h->native_dev, h->pace_dev, h->pace_rows, h->pace_stride, h->n_races, h->n_drivers, n_sims, sim_begin, seed, (flags & MCGP_F_EXACT_NORMAL) != 0,
                            (unsigned long long*)hist_dev, finish_dev, times_dev, (TraceRecord*)(trace_count ? trace_dev : nullptr),
-                           trace_first, trace_count, h->work_counter, h->sm_count, (cudaStream_t)cuda_stream));
+                           trace_first, trace_count, (unsigned long long*)laphist_dev, h->work_counter, h->sm_count,
+                           (cudaStream_t)cuda_stream));
     h->launches = 2;  // the claim-counter reset + the race kernel
     return MCGP_OK;
 }
@@ -384,6 +385,42 @@ int mcgp_launch_native_traced(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin
                               void* cuda_stream) {
     if (h && !trace_dev) return fail(h, MCGP_EINVAL, "trace_dev is NULL");
     return launch_native_common(h, n_sims, sim_begin, seed, flags, hist_dev, nullptr, nullptr, trace_dev, trace_first, trace_count, cuda_stream);
+}
+
+int mcgp_lap_histogram_laps(mcgp_handle h) { return h && h->native_dev ? h->pace_rows - 5 : 0; }
+
+int mcgp_launch_native_laphist(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
+                               uint64_t* hist_dev, uint64_t* laphist_dev, void* cuda_stream) {
+    if (h && !laphist_dev) return fail(h, MCGP_EINVAL, "laphist_dev is NULL");
+    if (h && h->native_dev) {
+        const size_t cells = (size_t)(h->pace_rows - 5) * h->n_drivers * h->n_drivers;
+        const size_t smem = ((size_t)h->pace_rows * h->pace_stride + MCGP_LANES) * sizeof(PaceEntry) + cells * 4;
+        if (smem > 180u * 1024u)
+            return fail(h, MCGP_EINVAL, "laps x drivers^2 too large: the lap histogram (4 B per cell) and the pace table must fit 180 KB of shared memory");
+    }
+    return launch_native_common(h, n_sims, sim_begin, seed, flags, hist_dev, nullptr, nullptr, nullptr, 0, 0, cuda_stream, laphist_dev);
+}
+
+int mcgp_run_native_laphist(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims, uint64_t sim_begin,
+                            uint64_t seed, uint32_t flags, uint64_t* hist_host, uint64_t* laphist_host) {
+    if (!h) return MCGP_EINVAL;
+    if (!hist_host || !laphist_host) return fail(h, MCGP_EINVAL, "NULL output pointer");
+    int rc = mcgp_upload_races(h, races, n_races);
+    if (rc) return rc;
+    const size_t n = (size_t)h->n_drivers;
+    const size_t hist_bytes = (size_t)n_races * n * n * sizeof(uint64_t);
+    const size_t lh_bytes = (size_t)n_races * (size_t)(h->pace_rows - 5) * n * n * sizeof(uint64_t);
+    void *hist_dev = nullptr, *lh_dev = nullptr;
+    if ((rc = scratch_get(h, 0, hist_bytes, &hist_dev))) return rc;
+    if ((rc = scratch_get(h, 6, lh_bytes, &lh_dev))) return rc;
+    CU(cudaMemcpy(hist_dev, hist_host, hist_bytes, cudaMemcpyHostToDevice));      // counts accumulate (+=)
+    CU(cudaMemcpy(lh_dev, laphist_host, lh_bytes, cudaMemcpyHostToDevice));
+    rc = mcgp_launch_native_laphist(h, n_sims, sim_begin, seed, flags, (uint64_t*)hist_dev, (uint64_t*)lh_dev, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpy(hist_host, hist_dev, hist_bytes, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(laphist_host, lh_dev, lh_bytes, cudaMemcpyDeviceToHost));
+    CU(cudaDeviceSynchronize());
+    return MCGP_OK;
 }
 
 int mcgp_run_native_traced(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims, uint64_t sim_begin,

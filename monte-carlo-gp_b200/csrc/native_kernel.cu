@@ -156,25 +156,31 @@ struct NativeOutputs {
     float* times;               // [race][sim][driver] final gap to the winner
     TraceRecord* trace;         // [race][sim - trace_first][lap][driver]
     unsigned long long trace_first, trace_count;  // window of sims (indices within the launch) that are traced
+    unsigned long long* laphist;  // [race][lap][driver][pos] running-position counts after every lap (kOut == 3)
+    int lh_cells;                 // laps x n x n of one race's lap histogram (laps = the longest race of the batch)
 };
 
-// kOut: 0 = count table only, 1 = + finish/times, 2 = + per-lap trace
-template <int NV4, bool kExact, int kOut>
-__global__ void __launch_bounds__(kThreads, MCGP_MIN_BLOCKS)
+// kOut: 0 = count table only, 1 = + finish/times, 2 = + per-lap trace, 3 = + per-lap position histogram (the on-chip
+// reduction of the trace: BASELINE config 5's alternative output).  kWarps: warps per block -- the lap histogram lives
+// in shared memory (laps x n x n counters: 91 KB for 57 laps x 20 cars), so that variant runs ONE block of 32 warps
+// per SM where the others run four blocks of eight.
+template <int NV4, bool kExact, int kOut, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, (MCGP_MIN_BLOCKS * MCGP_WARPS_PER_BLOCK) / kWarps)
 native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict__ ptab, const int pt_rows, const int pt_stride,
                    unsigned long long n_sims, unsigned long long sim_begin,
                    const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
                    const __grid_constant__ NativeOutputs out, unsigned long long* __restrict__ work_counter) {
-    constexpr bool kDetail = kOut >= 1, kTrace = kOut >= 2;
+    constexpr bool kDetail = kOut == 1 || kOut == 2, kTrace = kOut == 2, kLapHist = kOut == 3;
+    constexpr int kThr = kWarps * 32;
     constexpr bool kSmall = NV4 == 5;  // n <= 20: lanes 20..31 carry no car and lend their Philox words
     uint8_t* __restrict__ finish = out.finish;
     float* __restrict__ times = out.times;
     __shared__ NativeRace R;
     extern __shared__ __align__(16) uint4 PT[];  // overtake pace table [age][lane] (device_params.h: PaceEntry) + one row of padding
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
-    __shared__ __align__(16) float S_t_all[kWarpsPerBlock][32];
-    __shared__ float S_w_all[kWarpsPerBlock][48];              // window scratch: times by OLD rank, -inf / +inf pads
-    __shared__ __align__(16) float4 S_rec_all[kWarpsPerBlock][36];  // records by rank: {time, overtake pace, last lap, lane}
+    __shared__ __align__(16) float S_t_all[kWarps][32];
+    __shared__ float S_w_all[kWarps][48];              // window scratch: times by OLD rank, -inf / +inf pads
+    __shared__ __align__(16) float4 S_rec_all[kWarps][36];  // records by rank: {time, overtake pace, last lap, lane}
 
     // A block starts on race blockIdx.y of the batch and, when that race's sims are all claimed, hops to the next
     // race that still has work (a season batch mixes 44- and 78-lap races: without hopping the blocks of the short
@@ -191,11 +197,15 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(races + race);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&R);
-        for (int i = threadIdx.x; i < (int)(sizeof(NativeRace) / 4); i += kThreads) dst[i] = src[i];
-        for (int i = threadIdx.x; i < MCGP_LANES * MCGP_LANES; i += kThreads) hist_s[i] = 0;
+        for (int i = threadIdx.x; i < (int)(sizeof(NativeRace) / 4); i += kThr) dst[i] = src[i];
+        for (int i = threadIdx.x; i < MCGP_LANES * MCGP_LANES; i += kThr) hist_s[i] = 0;
         const int pt_n = pt_rows * pt_stride;
         const uint4* psrc = ptab + (size_t)race * pt_n;
-        for (int i = threadIdx.x; i < pt_n + MCGP_LANES; i += kThreads) PT[i] = i < pt_n ? psrc[i] : make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < pt_n + MCGP_LANES; i += kThr) PT[i] = i < pt_n ? psrc[i] : make_uint4(0u, 0u, 0u, 0u);
+        if (kLapHist) {
+            uint32_t* lh = reinterpret_cast<uint32_t*>(PT + pt_n + MCGP_LANES);
+            for (int i = threadIdx.x; i < out.lh_cells; i += kThr) lh[i] = 0u;
+        }
     }
     __syncthreads();
 
@@ -246,7 +256,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     // of its use.  The warp scheduler favours some warps over others, so an even static split left 20 % of the
     // warp-slots idle at the end; which warp runs which sim does not matter (draws are keyed by the sim index).
     unsigned long long* const claim = work_counter + race;
-    unsigned long long s = (unsigned long long)blockIdx.x * kWarpsPerBlock + (unsigned)warp;  // static first sim on the home race
+    unsigned long long s = (unsigned long long)blockIdx.x * kWarps + (unsigned)warp;  // static first sim on the home race
     if (hop > 0) {
         if (lane == 0) s = atomicAdd(claim, 1ull);
         s = __shfl_sync(FULL, s, 0);
@@ -419,9 +429,18 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             }
         };
 
+        // per-lap position histogram: every running car's position after the lap, one shared-memory atomic per car
+        auto count_lap = [&](const int lap, const bool dnf_now) {
+            if (kLapHist) {
+                const int pl = live_position(!dnf_now);
+                uint32_t* lh = reinterpret_cast<uint32_t*>(PT + pt_rows * pt_stride + MCGP_LANES);
+                if (is_car && !dnf_now) atomicAdd(&lh[((lap - 1) * n + lane) * n + pl], 1u);
+            }
+        };
         full_rank(dnf_lap <= 1 ? kNaN : 0.0f);
         update_positions(1, dnf_lap <= 1);
         emit_trace(1, dnf_lap <= 1);
+        count_lap(1, dnf_lap <= 1);
 
         // One lap >= 2.  z: this lap's pace noise; u12: overtake uniforms of passes 1 / 2 in the low / high half;
         // ext: pass 3 of the pair's even / odd lap in its low / high half; ev: the word that decides the race event
@@ -561,6 +580,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             if (!have_rank) full_rank(op32);
             update_positions(lap, dnf);
             emit_trace(lap, dnf);
+            count_lap(lap, dnf);
         };
 
         // One Philox call per lane per lap PAIR (made on the even lap): x, y -> Box-Muller pair (cos: this lap, sin:
@@ -621,9 +641,16 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     }
 
     __syncthreads();
-    for (int i = threadIdx.x; i < n * n; i += kThreads) {
+    for (int i = threadIdx.x; i < n * n; i += kThr) {
         const uint32_t v = hist_s[i];
         if (v) atomicAdd(&hist[(unsigned long long)race * n * n + i], (unsigned long long)v);
+    }
+    if (kLapHist) {
+        const uint32_t* lh = reinterpret_cast<const uint32_t*>(PT + pt_rows * pt_stride + MCGP_LANES);
+        for (int i = threadIdx.x; i < out.lh_cells; i += kThr) {
+            const uint32_t v = lh[i];
+            if (v) atomicAdd(&out.laphist[(unsigned long long)race * out.lh_cells + i], (unsigned long long)v);
+        }
     }
     }  // hop
 }
@@ -648,50 +675,53 @@ struct LaunchArgs {
     cudaStream_t st;
 };
 
-template <int NV4, bool kExact, int kOut>
+template <int NV4, bool kExact, int kOut, int kWarps>
 static cudaError_t launch_one(const LaunchArgs& a) {
-    auto kern = native_race_kernel<NV4, kExact, kOut>;
+    auto kern = native_race_kernel<NV4, kExact, kOut, kWarps>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.dyn_smem);
     if (e != cudaSuccess) return e;
-    // persistent-style grid: as many blocks as are resident at once (the register budget allows MCGP_MIN_BLOCKS per SM,
-    // a long race's pace table may allow fewer), split evenly over the races of the batch
+    // persistent-style grid: as many blocks as are resident at once (the register budget allows MCGP_MIN_BLOCKS blocks of
+    // MCGP_WARPS_PER_BLOCK warps per SM, a long race's pace table may allow fewer), split evenly over the races of the batch
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, a.dyn_smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarps * 32, a.dyn_smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const long long resident = (long long)a.sm_count * per_sm;
     long long bpr = resident / a.n_races;  // (never more blocks than fit at once: a waiting block could only start late)
-    const long long need = (long long)((a.n_sims + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const long long need = (long long)((a.n_sims + kWarps - 1) / kWarps);
     if (bpr > need) bpr = need;
     if (bpr < 1) bpr = 1;
-    const dim3 grid((unsigned)bpr, a.n_races), block(kThreads);
-    init_work_counters<<<1, 32, 0, a.st>>>(a.wc, a.n_races, (unsigned long long)bpr * kWarpsPerBlock);
+    const dim3 grid((unsigned)bpr, a.n_races), block(kWarps * 32);
+    init_work_counters<<<1, 32, 0, a.st>>>(a.wc, a.n_races, (unsigned long long)bpr * kWarps);
     kern<<<grid, block, a.dyn_smem, a.st>>>(a.races, a.ptab, a.pt_rows, a.pt_stride, a.n_sims, a.sim_begin, a.key, a.hist, a.out, a.wc);
     return cudaGetLastError();
 }
 
 template <int NV4, bool kExact>
 static cudaError_t launch_out(int kout, const LaunchArgs& a) {
-    if (kout == 0) return launch_one<NV4, kExact, 0>(a);
-    if (kout == 1) return launch_one<NV4, kExact, 1>(a);
-    return launch_one<NV4, kExact, 2>(a);
+    if (kout == 0) return launch_one<NV4, kExact, 0, kWarpsPerBlock>(a);
+    if (kout == 1) return launch_one<NV4, kExact, 1, kWarpsPerBlock>(a);
+    if (kout == 2) return launch_one<NV4, kExact, 2, kWarpsPerBlock>(a);
+    return launch_one<NV4, kExact, 3, kWarpsPerBlock * MCGP_MIN_BLOCKS>(a);
 }
 
 cudaError_t launch_native(const NativeRace* races_dev, const PaceEntry* pace_dev, int pace_rows, int pace_stride, int n_races,
                           int max_n, unsigned long long n_sims, unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
-                          unsigned long long trace_first, unsigned long long trace_count, unsigned long long* work_counter,
-                          int sm_count, cudaStream_t st) {
+                          unsigned long long trace_first, unsigned long long trace_count, unsigned long long* laphist,
+                          unsigned long long* work_counter, int sm_count, cudaStream_t st) {
     static_assert(sizeof(PaceEntry) == sizeof(uint4), "pace table entries are staged as 16-byte words");
-    const int kout = trace ? 2 : (finish != nullptr || times != nullptr) ? 1 : 0;
+    const int kout = laphist ? 3 : trace ? 2 : (finish != nullptr || times != nullptr) ? 1 : 0;
     LaunchArgs a;
     a.races = races_dev; a.ptab = reinterpret_cast<const uint4*>(pace_dev); a.pt_rows = pace_rows; a.pt_stride = pace_stride;
     a.n_sims = n_sims; a.sim_begin = sim_begin;
     a.key = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
     a.hist = hist;
-    a.out = NativeOutputs{finish, times, trace, trace_first, trace ? trace_count : 0ull};
+    const int lh_cells = laphist ? (pace_rows - 5) * max_n * max_n : 0;  // laps of the longest race x n x n
+    a.out = NativeOutputs{finish, times, trace, trace_first, trace ? trace_count : 0ull, laphist, lh_cells};
     a.wc = work_counter; a.n_races = n_races; a.sm_count = sm_count; a.st = st;
-    a.dyn_smem = ((size_t)pace_rows * pace_stride + MCGP_LANES) * sizeof(uint4);  // + one padding row (lanes without a car)
+    a.dyn_smem = ((size_t)pace_rows * pace_stride + MCGP_LANES) * sizeof(uint4)  // + one padding row (lanes without a car)
+                 + (size_t)lh_cells * sizeof(uint32_t);
     if (max_n <= 20) return exact ? launch_out<5, true>(kout, a) : launch_out<5, false>(kout, a);
     return exact ? launch_out<8, true>(kout, a) : launch_out<8, false>(kout, a);
 }

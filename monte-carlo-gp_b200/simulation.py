@@ -201,6 +201,20 @@ class RaceSimulator:
         hist = self._engine().run_native([params], int(n_simulations), sim_begin, self.last_seed, self.flags)
         return hist[0]
 
+    def run_monte_carlo_by_lap(self, n_simulations: int, grid_probs, base_pace, tire_deg, driver_variance,
+                               driver_dnf_rates=None, seed=None, track_condition='dry'):
+        """Extension (absent upstream): run_monte_carlo plus the running-position distribution after EVERY lap, reduced
+        on the GPU (no per-sim trace leaves the chip).  Returns ``(probabilities, by_lap)`` where ``probabilities`` is
+        run_monte_carlo's dict and ``by_lap`` a float64 array [total_laps, n_drivers, n_drivers]:
+        by_lap[lap-1, d, pos] = P(driver d runs in position pos+1 after lap `lap`); a row sums to P(d still running)."""
+        if n_simulations <= 0 or not grid_probs:
+            return {}, None
+        params = self._params(grid_probs, base_pace, tire_deg, driver_variance, driver_dnf_rates, track_condition)
+        self.last_seed = self._resolve_seed(seed)
+        hist, laphist = self._engine().run_native_laphist([params], int(n_simulations), 0, self.last_seed, self.flags)
+        return (counts_to_probabilities(hist[0], list(grid_probs.keys()), n_simulations),
+                laphist[0].astype(np.float64) / n_simulations)
+
     def simulate_race(self, grid: list[str], base_pace: dict[str, float], tire_deg: dict[str, float],
                       driver_variance: dict[str, float], driver_dnf_rates: dict[str, float] | None = None,
                       track_condition: str = 'dry') -> list[tuple[str, int]]:

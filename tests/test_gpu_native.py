@@ -121,6 +121,52 @@ def test_product_sized_calls_and_lap_limit(mcgp, oracle):
     assert np.array_equal(sim.run_monte_carlo_counts(10000, *args, seed=42), first)
 
 
+@pytest.mark.parametrize("case", ["bahrain_dry", "events", "attrition", "sprint19"])
+def test_lap_histogram_equals_trace_reduction(mcgp, oracle, case):
+    """The per-lap position histogram (the on-chip reduction of the trace, kernel variant with one 32-warp block per
+    SM) against the reduction of the scalar mirror's per-lap trace, cell by cell; its last lap must agree with the
+    finish table on the cars still running; the count table must equal the plain launch's."""
+    cfg, mc, seed, _ = gc.get_case(case)
+    eng = mcgp.capi.get_engine(0)
+    p = _params(mcgp, cfg, mc, stream=2)
+    n_sims, L, n = 6000, cfg["total_laps"], p.n_drivers
+    hist, lh = eng.run_native_laphist([p], n_sims, sim_begin=77, seed=seed, flags=mcgp.capi.F_EXACT_NORMAL)
+    assert lh.shape == (1, L, n, n)
+    ref = oracle.run_native(oracle.make_params(cfg, mc, *POP), seed, n_sims, sim_begin=77, stream=2, exact=True, trace=True)
+    tr = ref["trace"]                                   # [sim, lap, driver]
+    want = np.zeros((L, n, n), np.int64)
+    pos = tr["position"].astype(np.int64)
+    for lap in range(L):
+        for d in range(n):
+            c = np.bincount(pos[:, lap, d], minlength=n + 1)
+            want[lap, d, :] = c[1:]
+    assert np.array_equal(lh[0].astype(np.int64), want)
+    assert np.array_equal(hist[0].astype(np.int64), ref["hist"])
+    assert np.array_equal(hist, eng.run_native([p], n_sims, 77, seed, flags=mcgp.capi.F_EXACT_NORMAL))
+    # split invariance holds for the lap histogram too
+    h2, lh2 = eng.run_native_laphist([p], 1000, sim_begin=77, seed=seed, flags=mcgp.capi.F_EXACT_NORMAL)
+    h3, lh3 = eng.run_native_laphist([p], n_sims - 1000, sim_begin=1077, seed=seed, flags=mcgp.capi.F_EXACT_NORMAL)
+    assert np.array_equal(lh2 + lh3, lh) and np.array_equal(h2 + h3, hist)
+
+
+def test_lap_histogram_batch_and_api(mcgp):
+    eng = mcgp.capi.get_engine(0)
+    wl = mcgp.workloads
+    plist = [_params(mcgp, *wl.workload(f"season:{r}"), stream=r) for r in (0, 6, 12)]   # 57 / 70 / 52-lap races...
+    laps = max(p.total_laps for p in plist)
+    hist, lh = eng.run_native_laphist(plist, 4000, 0, 11)
+    assert lh.shape == (3, laps, 20, 20)
+    for i, p in enumerate(plist):
+        h1, l1 = eng.run_native_laphist([p], 4000, 0, 11)
+        assert np.array_equal(l1[0], lh[i, : p.total_laps]) and not lh[i, p.total_laps:].any()
+        assert np.array_equal(h1[0], hist[i])
+    cfg, mc = wl.workload("bahrain")
+    probs, by_lap = _sim(mcgp, cfg).run_monte_carlo_by_lap(50000, *[mc.get(k) for k in MC_KEYS], seed=5)
+    assert by_lap.shape == (57, 20, 20) and abs(by_lap[0].sum() - 20 * (1 - 0.008)) < 0.2
+    assert abs(by_lap[-1, 0, 0] - probs["VER"][1]) < 0.02      # leading after the last lap ~ winning (retirements aside)
+    assert np.all(by_lap.sum(2) <= 1 + 1e-12) and np.all(np.diff(by_lap.sum(2), axis=0) <= 1e-12)  # running share only falls
+
+
 def test_sim_range_split_invariance(mcgp):
     """Counter-based RNG keyed by the global sim index: [0,N) == [0,a) + [a,b) + [b,N) (the multi-GPU sharding)."""
     cfg, mc, seed, _ = gc.get_case("events")
