@@ -75,6 +75,27 @@ class ShardedSimulator:
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
         self.engine.launch_native(count, begin, seed, hist.data_ptr(), self.flags, stream=stream)
 
+    def run_by_lap(self, n_sims: int, seed: int, group=None):
+        """Like run(), plus the per-lap position histogram (include/mcgp.h: mcgp_launch_native_laphist).  Both tables
+        travel in ONE all-reduce (a flat int64 buffer [n_races * (n*n + laps*n*n)]); returns (hist, laphist) views."""
+        torch = self.torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.device)
+        laps = self.engine._lib.mcgp_lap_histogram_laps(self.engine._h)
+        n_h, n_l = self.n_races * self.n * self.n, self.n_races * laps * self.n * self.n
+        buf = torch.zeros(n_h + n_l, dtype=torch.int64, device=dev)
+        hist, laphist = buf[:n_h].view(self.n_races, self.n, self.n), buf[n_h:].view(self.n_races, laps, self.n, self.n)
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            rank, world = 0, 1
+        begin, count = shard_range(n_sims, rank, world)
+        if count:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.engine.launch_native_laphist(count, begin, seed, hist.data_ptr(), laphist.data_ptr(), self.flags, stream=stream)
+        all_reduce_counts(buf, group)
+        return hist, laphist
+
     def run(self, n_sims: int, seed: int, group=None):
         dev = self.torch.device("cuda", self.device)
         return run_sharded(n_sims, self.n_races, self.n, lambda b, c, h: self.launch(b, c, seed, h), group=group,

@@ -160,6 +160,9 @@ def test_lap_histogram_batch_and_api(mcgp):
         h1, l1 = eng.run_native_laphist([p], 4000, 0, 11)
         assert np.array_equal(l1[0], lh[i, : p.total_laps]) and not lh[i, p.total_laps:].any()
         assert np.array_equal(h1[0], hist[i])
+    sh = mcgp.distributed.ShardedSimulator(plist, device=0)          # device-resident front end, one all-reduce for both tables
+    hs, ls = sh.run_by_lap(4000, 11)
+    assert np.array_equal(hs.cpu().numpy().astype(np.uint64), hist) and np.array_equal(ls.cpu().numpy().astype(np.uint64), lh)
     cfg, mc = wl.workload("bahrain")
     probs, by_lap = _sim(mcgp, cfg).run_monte_carlo_by_lap(50000, *[mc.get(k) for k in MC_KEYS], seed=5)
     assert by_lap.shape == (57, 20, 20) and abs(by_lap[0].sum() - 20 * (1 - 0.008)) < 0.2
