@@ -163,6 +163,14 @@ static float* build_op32(const orc_params* p) {
     return tab;
 }
 
+int orc_native_op32_table(const orc_params* p, float* out) {
+    if (p->n_drivers < 1 || p->n_drivers > N32 || !out) return -1;
+    float* tab = build_op32(p);
+    memcpy(out, tab, sizeof(float) * (size_t)(p->total_laps + 5) * p->n_drivers);
+    free(tab);
+    return 0;
+}
+
 static void derive(const orc_params* p, nat_t* o) {
     memset(o, 0, sizeof(*o));
     int n = p->n_drivers;

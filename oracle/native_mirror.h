@@ -14,6 +14,11 @@ extern "C" {
 int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t sim_begin, int64_t n_sims, int exact,
                    int64_t* hist, uint8_t* finish, float* times, void* trace /* [n_sims][laps][n] 8-byte records, or NULL */);
 
+/* The mirror's overtake paces x 2^15 (FP32), out[(age * n + driver)] for age < total_laps + 5: the strictly increasing
+ * float images of the FP64 paces.  Exported so a CPU test can hold this construction against the library's own
+ * (mcgp_pace_table): the two are written independently and must agree bit for bit. */
+int orc_native_op32_table(const orc_params* p, float* out);
+
 #ifdef __cplusplus
 }
 #endif

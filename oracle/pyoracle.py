@@ -85,6 +85,8 @@ def lib():
         L.orc_run_native.argtypes = [C.POINTER(OrcParams), C.c_uint64, C.c_uint32, C.c_uint64, C.c_int64, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_run_native.restype = C.c_int
+        L.orc_native_op32_table.argtypes = [C.POINTER(OrcParams), C.c_void_p]
+        L.orc_native_op32_table.restype = C.c_int
         L.orc_py_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.orc_py_sum.restype = C.c_double
         _lib = L
@@ -258,6 +260,15 @@ def run_monte_carlo(cfg: dict, mc: dict, n_sims: int, seed: int | None, pop_no_m
 
 TRACE_DTYPE = np.dtype([("position", np.uint8), ("compound", np.uint8), ("tire_age", np.uint8), ("flags", np.uint8),
                         ("gap", np.float32)])
+
+
+def native_op32_table(params: OrcParams) -> np.ndarray:
+    """The mirror's overtake-pace table [total_laps + 5, n] (float32); see native_mirror.h."""
+    out = np.zeros((params.total_laps + 5, params.n_drivers), np.float32)
+    rc = lib().orc_native_op32_table(C.byref(params), _ptr(out))
+    if rc:
+        raise RuntimeError(f"orc_native_op32_table failed: {rc}")
+    return out
 
 
 def run_native(params: OrcParams, seed: int, n_sims: int, sim_begin: int = 0, stream: int = 0, exact: bool = True,

@@ -100,3 +100,15 @@ def test_table_on_random_and_degenerate_inputs(mcgp):
     m["base_pace"] = {d: 92.0 + 1e-9 * k for k, d in enumerate(D)}
     m["tire_deg"] = {d: 0.0 for d in D}
     _check(mcgp, dict(cfg, total_laps=5), m)
+
+
+@pytest.mark.parametrize("name", ["bahrain", "monaco_sc", "sprint19", "season:11"])
+def test_library_and_mirror_build_the_same_float_images(mcgp, name):
+    """The kernel's host-built table (C++, libmcgp.so) and the scalar mirror's (C, oracle/) are written independently;
+    the bit-exact kernel == mirror GPU tests rest on them being identical."""
+    from oracle import pyoracle as po
+    cfg, mc = mcgp.workloads.workload(name)
+    tab = mcgp.capi.pace_table(_params(mcgp, cfg, mc))
+    mir = po.native_op32_table(po.make_params(cfg, mc, "SOFT", "MEDIUM"))
+    n = mir.shape[1]
+    assert np.array_equal(tab[:, :n, 0].view(np.uint32), mir.view(np.uint32))
