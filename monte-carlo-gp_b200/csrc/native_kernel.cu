@@ -246,7 +246,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
     // cumulative event thresholds (red | SC | VSC share one draw); only the event lane ever sees a non-zero ev_any
     const int ev_lane = kSmall ? 31 : 0;
-    uint32_t ev_any = (!kSmall || lane == ev_lane) ? R.vsc_thr : 0u;
+    uint32_t ev_any = lane == ev_lane ? R.vsc_thr : 0u;
     asm volatile("" : "+r"(ev_any));  // keep it a per-lane register: one compare per lap instead of compare + lane test
     const uint32_t stream = __shfl_sync(FULL, R.stream, 0);
     const Tables tab{&R, lane};
@@ -585,8 +585,8 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
 
         // One Philox call per lane per lap PAIR (made on the even lap): x, y -> Box-Muller pair (cos: this lap, sin:
         // the next); z -> this lap's overtake passes 1, 2; w -> the next lap's; passes 3 come from a borrowed word.
-        // Event lane (31, or the virtual lane 64 when there are more than 20 cars): x, y -> the event draws of the
-        // two laps, z -> the two 16-bit VSC roll-back draws.
+        // Event lane (31; with more than 20 cars: words y, z, w of lane 0's second call): the event draws of the
+        // two laps and the two 16-bit VSC roll-back draws.
         // The loop runs over lap PAIRS with both lap bodies spelled out: which half of the pair's draws a lap uses is
         // then a compile-time fact (no per-lap parity tests, no hand-over moves: -8 instructions per lap), and the
         // scheduler can start the pair's Philox call under the previous lap's tail.  The price is a 40 KB kernel
@@ -600,9 +600,10 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             if (kSmall) {  // lanes 20..29 lend x (to drivers 0..9) and y (to drivers 10..19)
                 const uint32_t e1 = __shfl_down_sync(FULL, w.x, 20), e2 = __shfl_down_sync(FULL, w.y, 10);
                 ext = lane < 10 ? e1 : e2;
-            } else {  // up to 32 cars: a second call per lane, and one warp-uniform call for the events
-                ext = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)(lane + 32), stream, key).x;
-                ev = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | 64u, stream, key);
+            } else {  // up to 32 cars: a second call per lane; lane 0's spare words are the event draws
+                const uint4 xw = philox4x32_10(sim_lo, sim_hi, ((uint32_t)lap << 8) | (uint32_t)(lane + 32), stream, key);
+                ext = xw.x;
+                ev = make_uint4(xw.y, xw.z, xw.w, 0u);
             }
             float z, z_nx;  // this lap's / the next lap's pace noise
             if (kExact) exact_normal2(w.x, w.y, z, z_nx); else fast_normal2(w.x, w.y, z, z_nx);

@@ -13,7 +13,8 @@
  *              pass 3 of laps l / l+1 = lo / hi 16 bits of a borrowed word: n <= 20: word0 of lane 20+d (d < 10)
  *              or word1 of lane 10+d (d >= 10); n > 20: word0 of lane 32+d.
  *              events: red, else SC, else VSC decided by ONE word against cumulative thresholds -- word0 (lap l) /
- *              word1 (lap l+1) of lane 31 (n <= 20) or lane 64 (n > 20); VSC tyre roll-back: lo / hi 16 bits of word2
+ *              word1 (lap l+1) of lane 31, VSC tyre roll-back: lo / hi 16 bits of word2 (n <= 20); n > 20: words 1 / 2 / 3 of
+ *              lane 32's call (driver 0's second call, whose word0 is its pass-3 draw)
  *   - FP32, every fused op explicit (fmaf), times re-based on the leader after every lap,
  *     overtake chains in closed form  base - 0.1*(k - 2*sn), ordering by (time, driver index).
  * With the "exact" normal generator (IEEE-only arithmetic) kernel and mirror agree bit for bit; the
@@ -354,7 +355,9 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
         for (int lap = 2; lap <= L; lap++) {
             const uint32_t pair = (uint32_t)(lap & ~1), odd = (uint32_t)(lap & 1);
             /* ---- events :168-176 ---- */
-            const u4 we = philox(s0, s1, (pair << 8) | (n <= 20 ? 31u : 64u), stream, k0, k1);
+            /* n <= 20: lane 31's call, words x / y / z; more cars: the spare words y / z / w of driver 0's second call */
+            u4 we = philox(s0, s1, (pair << 8) | (n <= 20 ? 31u : 32u), stream, k0, k1);
+            if (n > 20) { we.x = we.y; we.y = we.z; we.z = we.w; }
             const uint32_t evw = odd ? we.y : we.x, roll = odd ? we.z >> 16 : we.z & 0xffffu;
             const int ev = evw < R.red_thr ? 1 : evw < R.sc_thr ? 2 : evw < R.vsc_thr ? (roll < 19660u ? 4 : 3) : 0;
             const int rem = L - lap;
