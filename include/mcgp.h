@@ -9,7 +9,12 @@
  * Conventions: plain C, no torch/CUDA types in signatures (streams and device buffers travel as
  * raw void / uint64_t pointers).  Every function returns 0 on success, a negative MCGP_E* code on
  * failure; mcgp_last_error() gives the message.  No exceptions cross the ABI.  The caller owns all
- * buffers.  One handle per device; calls on one handle must be serialised by the caller.
+ * buffers.  Host calls on one handle must be serialised by the caller (several handles per device are
+ * fine: each owns its parameter blocks and claim counters).  GPU work of one handle is ordered by the
+ * library itself: launches made through one handle run one after the other whatever streams they are
+ * given (they share the handle's claim counters), and mcgp_upload_races / the host-buffer calls wait
+ * for the handle's last launch before they overwrite the resident parameter blocks.  Every entry point
+ * restores the caller's current CUDA device before it returns.
  * There is NO CPU fallback: every entry point fails with MCGP_ENODEVICE when no sm_100 GPU is present.
  */
 #ifndef MCGP_H
@@ -54,7 +59,8 @@ enum {
 typedef struct mcgp_race_params {
     int32_t n_drivers;       /* 1..MCGP_MAX_DRIVERS                                              */
     int32_t total_laps;      /* RaceConfig.total_laps, 1..505 (n_drivers <= 20) / 1..314 (more):   *
-                              * the per-race overtake pace table must fit in shared memory      */
+                              * the per-race overtake pace table must fit in shared memory;     *
+                              * anything larger is rejected with MCGP_EINVAL at upload          */
     int32_t track_condition; /* MCGP_DRY / MCGP_DAMP / MCGP_WETTRACK                              */
     int32_t pop_no_medium;   /* `({S,M,H}-{M}).pop()`: MCGP_SOFT or MCGP_HARD  (src/simulation.py:486)  */
     int32_t pop_no_soft;     /* `({S,M,H}-{S}).pop()`: MCGP_MEDIUM or MCGP_HARD (src/simulation.py:488) */
@@ -88,7 +94,11 @@ const char* mcgp_last_error(mcgp_handle h);
 /* multiProcessorCount and current SM clock (kHz) of the context's device, for roofline arithmetic. */
 int mcgp_device_info(mcgp_handle h, int* sm_count, int* sm_clock_khz, int* cc_major, int* cc_minor);
 
-/* native mode: counter-based Philox4x32-10 keyed (seed ; sim, lap pair, lane, stream), FP32 ----- *
+/* Philox rounds the native kernels were built with (7: the fastest Crush-resistant Philox4x32 of the Random123 paper;
+ * -DMCGP_PHILOX_ROUNDS=10 at build time restores the paper's default). */
+int mcgp_native_philox_rounds(void);
+
+/* native mode: counter-based Philox4x32-7 keyed (seed ; sim, lap pair, lane, stream), FP32 ------ *
  * Replaces the loop of run_monte_carlo (src/simulation.py:83-94) for sims
  * [sim_begin, sim_begin + n_sims) of each of the n_races races; results do not depend on how a sim
  * range is split over calls or GPUs.
@@ -97,7 +107,9 @@ int mcgp_device_info(mcgp_handle h, int* sm_count, int* sm_clock_khz, int* cc_ma
  *   finish  optional, [n_races][n_sims][n] driver index per finishing position (:236-242).
  *   times   optional, [n_races][n_sims][n] float: final time behind the winner, per driver index. */
 
-/* Host-buffer form: parameters are copied in, counts copied out, the call is synchronous. */
+/* Host-buffer form: parameters are copied in, counts copied out, the call is synchronous.  A batch identical
+ * (byte for byte) to the one already resident on the handle is not derived or uploaded again.  At most 2^32 - 1
+ * sims per launch (all native entry points). */
 int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims,
                     uint64_t sim_begin, uint64_t seed, uint32_t flags, uint64_t* hist_host,
                     uint8_t* finish_host /* nullable */, float* times_host /* nullable */);
@@ -115,7 +127,7 @@ int mcgp_launch_native(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint6
 typedef struct mcgp_trace_record {
     uint8_t position; /* running position after the lap (1 = leader), 0 = retired                               */
     uint8_t compound; /* MCGP_SOFT .. MCGP_WET                                                                    */
-    uint8_t tire_age; /* laps on the current set                                                                  */
+    uint8_t tire_age; /* laps on the current set (saturates at 255)                                               */
     uint8_t flags;    /* bit0 retired, bit1 DRS armed for the next lap, bit2 pitted this lap, bits4-5 event this lap
                          (1 red flag, 2 safety car, 3 VSC)                                                         */
     float gap;        /* seconds behind the leader                                                                 */

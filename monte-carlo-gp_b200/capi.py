@@ -56,6 +56,7 @@ _lib = None
 
 _SIGNATURES = {
     "mcgp_abi_version": (C.c_int, []),
+    "mcgp_native_philox_rounds": (C.c_int, []),
     "mcgp_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "mcgp_destroy": (C.c_int, [C.c_void_p]),
     "mcgp_last_error": (C.c_char_p, [C.c_void_p]),
@@ -94,6 +95,8 @@ def load_library():
                 "This engine has no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
+            if not hasattr(lib, name) and os.environ.get("MCGP_LIB_PATH"):
+                continue  # an A/B build of an older kernel may lack newer entry points; the shipped library may not
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
         if lib.mcgp_abi_version() != 1:

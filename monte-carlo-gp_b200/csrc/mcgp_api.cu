@@ -24,6 +24,7 @@ cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
                           unsigned long long* work_counter, int sm_count, cudaStream_t st);
+int native_philox_rounds();
 }  // namespace mcgp
 
 struct mcgp_context {
@@ -38,15 +39,38 @@ struct mcgp_context {
     size_t cap_pace = 0;               // allocated capacity of pace_dev (entries)
     ReplayRace* replay_dev = nullptr;
     unsigned long long* work_counter = nullptr;  // one claim counter per race of the batch (dynamic sim distribution)
-    int n_races = 0, n_drivers = 0;
+    int n_races = 0, n_drivers = 0;    // the uploaded batch; n_races == 0: nothing (valid) is resident
+    bool replay_ready = false;         // replay_dev holds the blocks of the resident batch (derived lazily, see ensure_replay)
+    bool uniform_laps = true;          // every race of the resident batch has the same total_laps
     int launches = 0;
     uint64_t upload_bytes = 0;
+    std::vector<mcgp_race_params> resident;  // host copy of the resident batch: a repeated call with identical
+                                             // parameters (the product calls the same race again and again) skips
+                                             // the derivation and the upload
+    // Launches on one handle share the claim counters and the parameter blocks, so they are ordered against each other
+    // (and re-uploads against them) through this event, whatever stream the caller passes.
+    cudaEvent_t last_launch = nullptr;
+    bool launched = false;
+    cudaStream_t own_stream = nullptr;  // host-buffer entry points: async copies + kernel + ONE synchronisation
+    void* pinned = nullptr;             // grow-only pinned staging block of the host-buffer entry points
+    size_t pinned_sz = 0;
     // grow-only scratch for the host-buffer entry points
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_sz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;  // message of the calling thread's last failed mcgp_create
+
+// Every entry point runs on the context's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t status;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        status = prev == device ? cudaSuccess : cudaSetDevice(device);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static int fail(mcgp_handle h, int code, const std::string& msg) {
     if (h) h->err = msg; else g_create_error = msg;
@@ -91,9 +115,19 @@ static float dnf_scale(double rate) {
 
 static double clamp01(double p) { return !(p > 0.0) ? 0.0 : p > 1.0 ? 1.0 : p; }
 
+// laps the overtake pace table (rows = laps + 5, `stride` entries of 16 B per row, + one padding row) can hold in the
+// 160 KB of shared memory it is staged into
+static int max_laps_for(int n_drivers) {
+    const int stride = n_drivers <= 20 ? 20 : MCGP_LANES;
+    return (int)((160u * 1024u / sizeof(PaceEntry) - MCGP_LANES) / stride) - 5;   // 505 (<= 20 drivers), 314 (more)
+}
+
 static int validate(mcgp_handle h, const mcgp_race_params* r) {
     if (r->n_drivers < 1 || r->n_drivers > MCGP_MAX_DRIVERS) return fail(h, MCGP_EINVAL, "n_drivers must be in 1..32");
-    if (r->total_laps < 1 || r->total_laps > 65535) return fail(h, MCGP_EINVAL, "total_laps must be positive (and small enough for the pace table: 505 laps for <= 20 drivers, 314 for more)");
+    if (r->total_laps < 1) return fail(h, MCGP_EINVAL, "total_laps must be positive");
+    if (r->total_laps > max_laps_for(r->n_drivers))
+        return fail(h, MCGP_EINVAL, "total_laps too large: the overtake pace table (laps + 5 rows) must fit 160 KB of shared memory "
+                                    "(505 laps for <= 20 drivers, 314 for more)");
     if (r->track_condition < 0 || r->track_condition > 2) return fail(h, MCGP_EINVAL, "bad track_condition");
     if (!(r->pop_no_medium == MCGP_SOFT || r->pop_no_medium == MCGP_HARD)) return fail(h, MCGP_EINVAL, "pop_no_medium must be SOFT or HARD");
     if (!(r->pop_no_soft == MCGP_MEDIUM || r->pop_no_soft == MCGP_HARD)) return fail(h, MCGP_EINVAL, "pop_no_soft must be MEDIUM or HARD");
@@ -232,9 +266,146 @@ static void derive_replay(const mcgp_race_params* r, ReplayRace* o) {
 }
 
 // ---- ABI ------------------------------------------------------------------------------------
+// ---- resident batch management ------------------------------------------------------------------
+static void drop_resident(mcgp_handle h) {  // after a failed upload nothing may look valid
+    h->n_races = 0; h->n_drivers = 0; h->replay_ready = false; h->resident.clear();
+}
+
+static void free_blocks(mcgp_handle h) {
+    if (h->native_dev) { cudaFree(h->native_dev); h->native_dev = nullptr; }
+    if (h->replay_dev) { cudaFree(h->replay_dev); h->replay_dev = nullptr; }
+    if (h->work_counter) { cudaFree(h->work_counter); h->work_counter = nullptr; }
+    if (h->pace_dev) { cudaFree(h->pace_dev); h->pace_dev = nullptr; }
+    h->cap_races = 0; h->cap_pace = 0;
+    drop_resident(h);
+}
+
+static int pinned_get(mcgp_handle h, size_t bytes, void** out) {
+    if (h->pinned_sz < bytes) {
+        if (h->pinned) cudaFreeHost(h->pinned);
+        h->pinned = nullptr; h->pinned_sz = 0;
+        const size_t want = std::max(bytes, (size_t)1 << 16);
+        cudaError_t e = cudaMallocHost(&h->pinned, want);
+        if (e != cudaSuccess) return fail(h, MCGP_ENOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        h->pinned_sz = want;
+    }
+    *out = h->pinned;
+    return MCGP_OK;
+}
+
+// Wait (on the host) for the last launch this handle made before its blocks or counters are overwritten.
+static void wait_last_launch(mcgp_handle h) {
+    if (h->launched) { cudaEventSynchronize(h->last_launch); h->launched = false; }
+}
+
+// Derives and uploads the NATIVE blocks (parameter blocks + overtake pace tables) of a batch on `st`, staged through the
+// pinned block at `stage` (NULL: pageable temporaries + synchronous copies).  A batch identical to the resident one is
+// not derived or copied again.  The replay blocks are derived lazily (ensure_replay): the product path never replays.
+static int upload_native(mcgp_handle h, const mcgp_race_params* races, int n_races, cudaStream_t st, bool async) {
+    if (!races || n_races < 1) return fail(h, MCGP_EINVAL, "races is NULL or n_races < 1");
+    if (h->n_races == n_races && h->resident.size() == (size_t)n_races &&
+        memcmp(h->resident.data(), races, sizeof(mcgp_race_params) * (size_t)n_races) == 0) {
+        h->upload_bytes = 0;  // resident already: nothing crosses the bus
+        return MCGP_OK;
+    }
+    for (int r = 0; r < n_races; r++) {
+        int rc = validate(h, &races[r]);
+        if (rc) return rc;
+        if (races[r].n_drivers != races[0].n_drivers) return fail(h, MCGP_EINVAL, "all races of a batch must have the same n_drivers");
+    }
+    int rows = 0;
+    bool uniform = true;
+    for (int r = 0; r < n_races; r++) {
+        rows = std::max(rows, pace_rows(races[r].total_laps));
+        uniform = uniform && races[r].total_laps == races[0].total_laps;
+    }
+    const int stride = races[0].n_drivers <= 20 ? 20 : MCGP_LANES;
+    const size_t per_race = (size_t)rows * stride;
+    const size_t b_nat = sizeof(NativeRace) * (size_t)n_races, b_pace = sizeof(PaceEntry) * per_race * n_races;
+    wait_last_launch(h);  // in-flight kernels still read the old blocks
+    drop_resident(h);
+    // host staging: pinned (async path) or a plain temporary
+    std::vector<char> tmp;
+    char* stage = nullptr;
+    if (async) {
+        void* pin = nullptr;
+        // (room behind the staging area for the count tables mcgp_run_native sends through the same block)
+        int rc = pinned_get(h, ((b_nat + b_pace + 4095) & ~(size_t)4095) + (size_t)n_races * MCGP_LANES * MCGP_LANES * 8, &pin);
+        if (rc) return rc;
+        stage = (char*)pin;
+    } else {
+        try { tmp.resize(b_nat + b_pace); } catch (...) { return fail(h, MCGP_ENOMEM, "out of host memory"); }
+        stage = tmp.data();
+    }
+    NativeRace* nat = reinterpret_cast<NativeRace*>(stage);
+    PaceEntry* pace = reinterpret_cast<PaceEntry*>(stage + b_nat);
+    for (int r = 0; r < n_races; r++) {
+        derive_native(&races[r], &nat[r]);
+        build_pace_table(&races[r], rows, stride, pace + per_race * r);
+    }
+    // device blocks are grow-only: a product-sized call (10 000 sims = 0.13 ms of kernel) must not pay for cudaMalloc / cudaFree
+    cudaError_t e = cudaSuccess;
+    if (n_races > h->cap_races) {
+        if (h->native_dev) { cudaFree(h->native_dev); h->native_dev = nullptr; }
+        if (h->replay_dev) { cudaFree(h->replay_dev); h->replay_dev = nullptr; }
+        if (h->work_counter) { cudaFree(h->work_counter); h->work_counter = nullptr; }
+        h->cap_races = 0;
+        e = cudaMalloc(&h->native_dev, sizeof(NativeRace) * n_races);
+        if (e == cudaSuccess) e = cudaMalloc(&h->work_counter, sizeof(unsigned long long) * n_races);
+        if (e == cudaSuccess) e = cudaMalloc(&h->replay_dev, sizeof(ReplayRace) * n_races);
+        if (e == cudaSuccess) h->cap_races = n_races;
+    }
+    if (e == cudaSuccess && per_race * n_races > h->cap_pace) {
+        if (h->pace_dev) { cudaFree(h->pace_dev); h->pace_dev = nullptr; }
+        h->cap_pace = 0;
+        e = cudaMalloc(&h->pace_dev, b_pace);
+        if (e == cudaSuccess) h->cap_pace = per_race * n_races;
+    }
+    if (e == cudaSuccess) e = async ? cudaMemcpyAsync(h->native_dev, nat, b_nat, cudaMemcpyHostToDevice, st)
+                                    : cudaMemcpy(h->native_dev, nat, b_nat, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = async ? cudaMemcpyAsync(h->pace_dev, pace, b_pace, cudaMemcpyHostToDevice, st)
+                                    : cudaMemcpy(h->pace_dev, pace, b_pace, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {  // leave nothing half-initialised behind: a later launch must fail cleanly, not run on garbage
+        free_blocks(h);
+        return fail(h, MCGP_ECUDA, std::string("upload: ") + cudaGetErrorString(e));
+    }
+    try { h->resident.assign(races, races + n_races); } catch (...) { drop_resident(h); return fail(h, MCGP_ENOMEM, "out of host memory"); }
+    h->n_races = n_races; h->n_drivers = races[0].n_drivers;
+    h->pace_rows = rows; h->pace_stride = stride; h->uniform_laps = uniform;
+    h->upload_bytes = b_nat + b_pace;
+    return MCGP_OK;
+}
+
+// The FP64 blocks of the resident batch, derived and uploaded the first time a replay needs them.
+static int ensure_replay(mcgp_handle h) {
+    if (h->replay_ready) return MCGP_OK;
+    if (h->n_races < 1) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
+    std::vector<ReplayRace> rep;
+    try { rep.resize(h->n_races); } catch (...) { return fail(h, MCGP_ENOMEM, "out of host memory"); }
+    for (int r = 0; r < h->n_races; r++) derive_replay(&h->resident[r], &rep[r]);
+    wait_last_launch(h);
+    cudaError_t e = cudaMemcpy(h->replay_dev, rep.data(), sizeof(ReplayRace) * h->n_races, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("upload (replay blocks): ") + cudaGetErrorString(e));
+    h->replay_ready = true;
+    h->upload_bytes += sizeof(ReplayRace) * (uint64_t)h->n_races;
+    return MCGP_OK;
+}
+
+// Launches on one handle are ordered against each other whatever stream they are given: they share the claim counters.
+static cudaError_t order_before(mcgp_handle h, cudaStream_t st) {
+    return h->launched ? cudaStreamWaitEvent(st, h->last_launch, 0) : cudaSuccess;
+}
+static cudaError_t order_after(mcgp_handle h, cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(h->last_launch, st);
+    if (e == cudaSuccess) h->launched = true;
+    return e;
+}
+
+// ---- ABI ------------------------------------------------------------------------------------
 extern "C" {
 
 int mcgp_abi_version(void) { return MCGP_ABI_VERSION; }
+int mcgp_native_philox_rounds(void) { return mcgp::native_philox_rounds(); }
 
 int mcgp_create(mcgp_handle* out, int device) {
     mcgp_handle h = nullptr;
@@ -255,20 +426,28 @@ int mcgp_create(mcgp_handle* out, int device) {
     h = new (std::nothrow) mcgp_context();
     if (!h) return fail(nullptr, MCGP_ENOMEM, "out of host memory");
     h->device = device; h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) { delete h; return fail(nullptr, MCGP_ENODEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+    DeviceGuard g(device);
+    e = g.status;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->last_launch, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        if (h->last_launch) cudaEventDestroy(h->last_launch);
+        delete h;
+        return fail(nullptr, MCGP_ENODEVICE, std::string("context setup: ") + cudaGetErrorString(e));
+    }
     *out = h;
     return MCGP_OK;
 }
 
 int mcgp_destroy(mcgp_handle h) {
     if (!h) return MCGP_OK;
-    cudaSetDevice(h->device);
-    if (h->native_dev) cudaFree(h->native_dev);
-    if (h->pace_dev) cudaFree(h->pace_dev);
-    if (h->replay_dev) cudaFree(h->replay_dev);
-    if (h->work_counter) cudaFree(h->work_counter);
+    DeviceGuard g(h->device);
+    wait_last_launch(h);
+    free_blocks(h);
     for (int i = 0; i < 8; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->last_launch) cudaEventDestroy(h->last_launch);
     delete h;
     return MCGP_OK;
 }
@@ -291,8 +470,8 @@ uint64_t mcgp_last_upload_bytes(mcgp_handle h) { return h ? h->upload_bytes : 0;
 
 int mcgp_pace_table(const mcgp_race_params* race, int32_t* rows, int32_t* stride, float* out) {
     if (!race || race->n_drivers < 1 || race->n_drivers > MCGP_MAX_DRIVERS || race->total_laps < 1) return MCGP_EINVAL;
+    if (race->total_laps > max_laps_for(race->n_drivers)) return MCGP_EINVAL;  // same limit as mcgp_upload_races
     const int r = pace_rows(race->total_laps), st = race->n_drivers <= 20 ? 20 : MCGP_LANES;
-    if (((size_t)r * st + MCGP_LANES) * sizeof(PaceEntry) > 160u * 1024u) return MCGP_EINVAL;  // same limit as mcgp_upload_races
     if (rows) *rows = r;
     if (stride) *stride = st;
     if (out) {
@@ -304,73 +483,34 @@ int mcgp_pace_table(const mcgp_race_params* race, int32_t* rows, int32_t* stride
 
 int mcgp_upload_races(mcgp_handle h, const mcgp_race_params* races, int n_races) {
     if (!h) return MCGP_EINVAL;
-    if (!races || n_races < 1) return fail(h, MCGP_EINVAL, "races is NULL or n_races < 1");
-    for (int r = 0; r < n_races; r++) {
-        int rc = validate(h, &races[r]);
-        if (rc) return rc;
-        if (races[r].n_drivers != races[0].n_drivers) return fail(h, MCGP_EINVAL, "all races of a batch must have the same n_drivers");
-    }
-    CU(cudaSetDevice(h->device));
-    NativeRace* nat = new (std::nothrow) NativeRace[n_races];
-    ReplayRace* rep = new (std::nothrow) ReplayRace[n_races];
-    if (!nat || !rep) { delete[] nat; delete[] rep; return fail(h, MCGP_ENOMEM, "out of host memory"); }
-    for (int r = 0; r < n_races; r++) { derive_native(&races[r], &nat[r]); derive_replay(&races[r], &rep[r]); }
-    int rows = 0;
-    for (int r = 0; r < n_races; r++) rows = std::max(rows, pace_rows(races[r].total_laps));
-    const int stride = races[0].n_drivers <= 20 ? 20 : MCGP_LANES;
-    const size_t per_race = (size_t)rows * stride;
-    if ((per_race + MCGP_LANES) * sizeof(PaceEntry) > 160u * 1024u) {  // the table is staged in shared memory next to 18 KB of state
-        delete[] nat; delete[] rep;
-        return fail(h, MCGP_EINVAL, "total_laps too large: the overtake pace table (laps + 5 rows) must fit 160 KB of shared memory");
-    }
-    std::vector<PaceEntry> pace;
-    try { pace.resize(per_race * n_races); } catch (...) { delete[] nat; delete[] rep; return fail(h, MCGP_ENOMEM, "out of host memory"); }
-    for (int r = 0; r < n_races; r++) build_pace_table(&races[r], rows, stride, pace.data() + per_race * r);
-    // device blocks are grow-only: a product-sized call (10 000 sims = 0.13 ms of kernel) must not pay for cudaMalloc / cudaFree
-    cudaError_t e = cudaSuccess;
-    if (n_races > h->cap_races) {
-        if (h->native_dev) { cudaFree(h->native_dev); h->native_dev = nullptr; }
-        if (h->replay_dev) { cudaFree(h->replay_dev); h->replay_dev = nullptr; }
-        if (h->work_counter) { cudaFree(h->work_counter); h->work_counter = nullptr; }
-        h->cap_races = 0;
-        e = cudaMalloc(&h->native_dev, sizeof(NativeRace) * n_races);
-        if (e == cudaSuccess) e = cudaMalloc(&h->work_counter, sizeof(unsigned long long) * n_races);
-        if (e == cudaSuccess) e = cudaMalloc(&h->replay_dev, sizeof(ReplayRace) * n_races);
-        if (e == cudaSuccess) h->cap_races = n_races;
-    }
-    if (e == cudaSuccess && pace.size() > h->cap_pace) {
-        if (h->pace_dev) { cudaFree(h->pace_dev); h->pace_dev = nullptr; }
-        h->cap_pace = 0;
-        e = cudaMalloc(&h->pace_dev, sizeof(PaceEntry) * pace.size());
-        if (e == cudaSuccess) h->cap_pace = pace.size();
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(h->native_dev, nat, sizeof(NativeRace) * n_races, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(h->pace_dev, pace.data(), sizeof(PaceEntry) * pace.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(h->replay_dev, rep, sizeof(ReplayRace) * n_races, cudaMemcpyHostToDevice);
-    delete[] nat; delete[] rep;
-    if (e != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("upload: ") + cudaGetErrorString(e));
-    h->n_races = n_races; h->n_drivers = races[0].n_drivers;
-    h->pace_rows = rows; h->pace_stride = stride;
-    h->upload_bytes = (sizeof(NativeRace) + sizeof(ReplayRace)) * (uint64_t)n_races + sizeof(PaceEntry) * (uint64_t)pace.size();
-    return MCGP_OK;
+    DeviceGuard g(h->device);
+    if (g.status != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(g.status));
+    return upload_native(h, races, n_races, nullptr, false);
 }
 
 static int launch_native_common(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
                                 uint64_t* hist_dev, uint8_t* finish_dev, float* times_dev, mcgp_trace_record* trace_dev,
                                 uint64_t trace_first, uint64_t trace_count, void* cuda_stream, uint64_t* laphist_dev = nullptr) {
     if (!h) return MCGP_EINVAL;
-    if (!h->native_dev) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
+    if (!h->native_dev || h->n_races < 1) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
     if (!hist_dev) return fail(h, MCGP_EINVAL, "hist_dev is NULL");
     h->launches = 0;
     if (n_sims == 0) return MCGP_OK;
+    // the per-block count tables are 32-bit (shared memory), flushed once per block: a block cannot see 2^32 sims
+    if (n_sims > 0xffffffffull) return fail(h, MCGP_EINVAL, "at most 2^32 - 1 sims per launch: split the range over several launches");
     if (trace_dev && (trace_first > n_sims || trace_count > n_sims - trace_first))
         return fail(h, MCGP_EINVAL, "trace window exceeds the launched sim range");
-    CU(cudaSetDevice(h->device));
+    if (trace_dev && trace_count && !h->uniform_laps)  // the trace is laid out [race][sim][lap][driver] with ONE lap count
+        return fail(h, MCGP_EINVAL, "traced batches need equal total_laps");
+    DeviceGuard g(h->device);
+    if (g.status != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(g.status));
     static_assert(sizeof(mcgp_trace_record) == sizeof(TraceRecord) && sizeof(TraceRecord) == 8, "trace record layout");
+    const cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU(order_before(h, st));
     CU(mcgp::launch_native(h->native_dev, h->pace_dev, h->pace_rows, h->pace_stride, h->n_races, h->n_drivers, n_sims, sim_begin, seed, (flags & MCGP_F_EXACT_NORMAL) != 0,
                            (unsigned long long*)hist_dev, finish_dev, times_dev, (TraceRecord*)(trace_count ? trace_dev : nullptr),
-                           trace_first, trace_count, (unsigned long long*)laphist_dev, h->work_counter, h->sm_count,
-                           (cudaStream_t)cuda_stream));
+                           trace_first, trace_count, (unsigned long long*)laphist_dev, h->work_counter, h->sm_count, st));
+    CU(order_after(h, st));
     h->launches = 2;  // the claim-counter reset + the race kernel
     return MCGP_OK;
 }
@@ -387,12 +527,12 @@ int mcgp_launch_native_traced(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin
     return launch_native_common(h, n_sims, sim_begin, seed, flags, hist_dev, nullptr, nullptr, trace_dev, trace_first, trace_count, cuda_stream);
 }
 
-int mcgp_lap_histogram_laps(mcgp_handle h) { return h && h->native_dev ? h->pace_rows - 5 : 0; }
+int mcgp_lap_histogram_laps(mcgp_handle h) { return h && h->native_dev && h->n_races > 0 ? h->pace_rows - 5 : 0; }
 
 int mcgp_launch_native_laphist(mcgp_handle h, uint64_t n_sims, uint64_t sim_begin, uint64_t seed, uint32_t flags,
                                uint64_t* hist_dev, uint64_t* laphist_dev, void* cuda_stream) {
     if (h && !laphist_dev) return fail(h, MCGP_EINVAL, "laphist_dev is NULL");
-    if (h && h->native_dev) {
+    if (h && h->native_dev && h->n_races > 0) {
         const size_t cells = (size_t)(h->pace_rows - 5) * h->n_drivers * h->n_drivers;
         const size_t smem = ((size_t)h->pace_rows * h->pace_stride + MCGP_LANES) * sizeof(PaceEntry) + cells * 4;
         if (smem > 180u * 1024u)
@@ -407,6 +547,7 @@ int mcgp_run_native_laphist(mcgp_handle h, const mcgp_race_params* races, int n_
     if (!hist_host || !laphist_host) return fail(h, MCGP_EINVAL, "NULL output pointer");
     int rc = mcgp_upload_races(h, races, n_races);
     if (rc) return rc;
+    DeviceGuard g(h->device);
     const size_t n = (size_t)h->n_drivers;
     const size_t hist_bytes = (size_t)n_races * n * n * sizeof(uint64_t);
     const size_t lh_bytes = (size_t)n_races * (size_t)(h->pace_rows - 5) * n * n * sizeof(uint64_t);
@@ -428,13 +569,15 @@ int mcgp_run_native_traced(mcgp_handle h, const mcgp_race_params* races, int n_r
                            uint64_t trace_first, uint64_t trace_count) {
     if (!h) return MCGP_EINVAL;
     if (!hist_host || !trace_host) return fail(h, MCGP_EINVAL, "NULL output pointer");
+    if (!races || n_races < 1) return fail(h, MCGP_EINVAL, "races is NULL or n_races < 1");
+    for (int r = 1; r < n_races; r++)
+        if (races[r].total_laps != races[0].total_laps) return fail(h, MCGP_EINVAL, "traced batches need equal total_laps");
     int rc = mcgp_upload_races(h, races, n_races);
     if (rc) return rc;
+    DeviceGuard g(h->device);
     const size_t n = (size_t)h->n_drivers;
     const size_t hist_bytes = (size_t)n_races * n * n * sizeof(uint64_t);
     const size_t tr_bytes = (size_t)n_races * trace_count * (size_t)races[0].total_laps * n * sizeof(mcgp_trace_record);
-    for (int r = 1; r < n_races; r++)
-        if (races[r].total_laps != races[0].total_laps) return fail(h, MCGP_EINVAL, "traced batches need equal total_laps");
     void *hist_dev = nullptr, *tr_dev = nullptr;
     if ((rc = scratch_get(h, 0, hist_bytes, &hist_dev))) return rc;
     if ((rc = scratch_get(h, 6, tr_bytes, &tr_dev))) return rc;
@@ -448,11 +591,17 @@ int mcgp_run_native_traced(mcgp_handle h, const mcgp_race_params* races, int n_r
     return MCGP_OK;
 }
 
+// The product call (src/predictor.py:283-291 makes it with 10 000 sims: 0.13 ms of kernel): parameters derived only
+// when they differ from the resident batch, everything staged through ONE pinned block, async copies and the two
+// launches on the handle's own stream, ONE synchronisation.
 int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims, uint64_t sim_begin,
                     uint64_t seed, uint32_t flags, uint64_t* hist_host, uint8_t* finish_host, float* times_host) {
     if (!h) return MCGP_EINVAL;
     if (!hist_host) return fail(h, MCGP_EINVAL, "hist_host is NULL");
-    int rc = mcgp_upload_races(h, races, n_races);
+    DeviceGuard g(h->device);
+    if (g.status != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(g.status));
+    const cudaStream_t st = h->own_stream;
+    int rc = upload_native(h, races, n_races, st, true);   // (stages through the front of the pinned block)
     if (rc) return rc;
     const size_t n = (size_t)h->n_drivers;
     const size_t hist_bytes = (size_t)n_races * n * n * sizeof(uint64_t);
@@ -462,13 +611,26 @@ int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, u
     if ((rc = scratch_get(h, 0, hist_bytes, &hist_dev))) return rc;
     if (finish_host && (rc = scratch_get(h, 1, fin_bytes, &fin_dev))) return rc;
     if (times_host && (rc = scratch_get(h, 6, tim_bytes, &tim_dev))) return rc;
-    CU(cudaMemcpy(hist_dev, hist_host, hist_bytes, cudaMemcpyHostToDevice));  // counts accumulate (+=)
-    rc = mcgp_launch_native(h, n_sims, sim_begin, seed, flags, (uint64_t*)hist_dev, (uint8_t*)fin_dev, (float*)tim_dev, nullptr);
+    // the count table travels through the pinned block BEHIND the parameter staging area (which the async upload of
+    // this very call may still be reading)
+    const size_t stage_off = (sizeof(NativeRace) * (size_t)n_races + sizeof(PaceEntry) * (size_t)h->pace_rows * h->pace_stride * n_races + 4095) & ~(size_t)4095;
+    void* pin = nullptr;
+    if (h->pinned_sz < stage_off + hist_bytes) {
+        // growing the block would free memory an in-flight copy reads: finish the upload first
+        CU(cudaStreamSynchronize(st));
+        if ((rc = pinned_get(h, stage_off + hist_bytes, &pin))) return rc;
+    }
+    pin = h->pinned;
+    uint64_t* hist_pin = reinterpret_cast<uint64_t*>((char*)pin + stage_off);
+    memcpy(hist_pin, hist_host, hist_bytes);
+    CU(cudaMemcpyAsync(hist_dev, hist_pin, hist_bytes, cudaMemcpyHostToDevice, st));  // counts accumulate (+=)
+    rc = launch_native_common(h, n_sims, sim_begin, seed, flags, (uint64_t*)hist_dev, (uint8_t*)fin_dev, (float*)tim_dev, nullptr, 0, 0, st);
     if (rc) return rc;
-    CU(cudaMemcpy(hist_host, hist_dev, hist_bytes, cudaMemcpyDeviceToHost));
-    if (finish_host && fin_bytes) CU(cudaMemcpy(finish_host, fin_dev, fin_bytes, cudaMemcpyDeviceToHost));
-    if (times_host && tim_bytes) CU(cudaMemcpy(times_host, tim_dev, tim_bytes, cudaMemcpyDeviceToHost));
-    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyAsync(hist_pin, hist_dev, hist_bytes, cudaMemcpyDeviceToHost, st));
+    if (finish_host && fin_bytes) CU(cudaMemcpyAsync(finish_host, fin_dev, fin_bytes, cudaMemcpyDeviceToHost, st));
+    if (times_host && tim_bytes) CU(cudaMemcpyAsync(times_host, tim_dev, tim_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(hist_host, hist_pin, hist_bytes);
     return MCGP_OK;
 }
 
@@ -476,15 +638,21 @@ int mcgp_launch_replay(mcgp_handle h, uint64_t n_sims, const double* u_py_dev, c
                        const int64_t* off_dev, uint64_t* hist_dev, uint8_t* finish_dev, double* times_dev,
                        int16_t* dnf_lap_dev, uint8_t* grid_dev, int64_t* used_dev, int32_t* status_dev, void* cuda_stream) {
     if (!h) return MCGP_EINVAL;
-    if (!h->replay_dev) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
+    if (!h->replay_dev || h->n_races < 1) return fail(h, MCGP_EINVAL, "mcgp_upload_races has not been called");
     if (h->n_races != 1) return fail(h, MCGP_EINVAL, "replay mode takes exactly one race");
     if (!hist_dev || !off_dev || !u_py_dev || !z_dev || !u_np_dev) return fail(h, MCGP_EINVAL, "NULL tape/hist pointer");
     h->launches = 0;
     if (n_sims == 0) return MCGP_OK;
-    CU(cudaSetDevice(h->device));
+    DeviceGuard g(h->device);
+    if (g.status != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(g.status));
+    int rc = ensure_replay(h);
+    if (rc) return rc;
+    const cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU(order_before(h, st));
     CU(mcgp::launch_replay(h->replay_dev, n_sims, u_py_dev, z_dev, u_np_dev, (const long long*)off_dev,
                            (unsigned long long*)hist_dev, finish_dev, times_dev, dnf_lap_dev, grid_dev,
-                           (long long*)used_dev, status_dev, h->work_counter, h->sm_count, (cudaStream_t)cuda_stream));
+                           (long long*)used_dev, status_dev, h->work_counter, h->sm_count, st));
+    CU(order_after(h, st));
     h->launches = 2;  // the claim-counter reset + the replay kernel
     return MCGP_OK;
 }
@@ -496,6 +664,7 @@ int mcgp_run_replay(mcgp_handle h, const mcgp_race_params* race, uint64_t n_sims
     if (!race || !off || !hist_host) return fail(h, MCGP_EINVAL, "NULL argument");
     int rc = mcgp_upload_races(h, race, 1);
     if (rc) return rc;
+    DeviceGuard g(h->device);
     const size_t n = (size_t)h->n_drivers;
     const int64_t* end = off + 3 * n_sims;
     const size_t b_py = (size_t)end[0] * 8, b_z = (size_t)end[1] * 8, b_np = (size_t)end[2] * 8;

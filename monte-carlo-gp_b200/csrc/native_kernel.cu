@@ -45,6 +45,9 @@ namespace mcgp {
 #ifndef MCGP_WARPS_PER_BLOCK
 #define MCGP_WARPS_PER_BLOCK 8
 #endif
+#ifndef MCGP_PIT_GUESS
+#define MCGP_PIT_GUESS 1  // pit stops repair the rank guess (see run_lap); 0 = the round-1 behaviour
+#endif
 constexpr int kWarpsPerBlock = MCGP_WARPS_PER_BLOCK;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned FULL = 0xffffffffu;
@@ -57,6 +60,15 @@ constexpr uint32_t kVscRoll16 = 19660u;  // floor(0.3 * 2^16)
 // (a NOP), not a WARPSYNC.  An empty asm with a memory clobber is NOT enough: ptxas reorders a thread's LDS above
 // its own STS to a different address.
 #define WARP_FENCE() __syncwarp()
+// -DMCGP_STRICT_FENCES: additionally put a __syncwarp() between every shared-memory store and the cross-lane load that
+// follows it in the record / window exchanges (XCHG_FENCE below).  The default build relies on the volatile accessors
+// instead (in-order LDS/STS issue of a convergent warp); the strict build is the memory-model-clean variant the
+// GPU tests hold the default build against, bit for bit (tests/test_gpu_native.py::test_strict_fence_build_is_identical).
+#ifdef MCGP_STRICT_FENCES
+#define XCHG_FENCE() __syncwarp()
+#else
+#define XCHG_FENCE() ((void)0)
+#endif
 
 // Shared-memory accessors on 32-bit shared addresses.  `volatile` keeps ptxas from reordering a lane's LDS above
 // its own STS to another address (which it otherwise does: the two never alias for ONE thread), so inside
@@ -241,8 +253,8 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     const uint32_t rowb = 16u * (uint32_t)__shfl_sync(FULL, pt_stride, 0);
     // (values needed once per race or only on rare paths -- retirement law, pit loss, red / SC thresholds -- are read
     // from the shared parameter block where they are used: the hot loop has no register to spare for them)
-    const float drs_delta = R.drs_delta;
-    const float drs32_on = R.drs32;
+    const float ndrs_delta = -R.drs_delta;
+    const float ndrs32 = -R.drs32;
     const float dirty_thr = R.dirty_thr, dirty_pen = R.dirty_pen;
     // cumulative event thresholds (red | SC | VSC share one draw); only the event lane ever sees a non-zero ev_any
     const int ev_lane = kSmall ? 31 : 0;
@@ -292,8 +304,8 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 int sel = __ffs(m) - 1;
                 if (m == 0u) {  // rare: total == 0 (:127-130, uniform over the remaining drivers) or u * total rounded up to total
                     const uint32_t rem_mask = __ballot_sync(FULL, remaining);
-                    if (total > 0.0f) {
-                        sel = 31 - __clz(rem_mask);
+                    if (total > 0.0f) {  // the last remaining driver that has probability mass
+                        sel = 31 - __clz(__ballot_sync(FULL, p > 0.0f));
                     } else {
                         const int nrem = __popc(rem_mask);
                         int k = (int)__fmul_rn(u, (float)nrem);
@@ -352,8 +364,9 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
         uint32_t ra;           // shared address of REC[rank]
         float4 prev;           // record of the car one rank ahead (REC[rank - 1]), valid whenever have_rank
         bool have_rank;        // warp-uniform: rank / bit / wa / ra / prev / REC describe the current times
-        float drs_f = 0.0f, drs32 = 0.0f;  // drs_delta (and x 2^15) while DRS is enabled for this car, else 0
+        float drsf = 0.0f;                 // 1.0f while DRS is enabled for this car, else 0.0f: fma(drsf, -delta, x) == x - delta / x
         uint32_t thr_sel = 0x3210u;        // PRMT selector: the no-DRS (first operand) or the DRS (second operand) threshold
+        float dthr = -kInf;                // dirty_thr while a car with a positive last lap runs ahead, else -inf (:208-216)
         float fuel = 0.0f;     // (110 - fuel_load) * 0.03 of the current lap: every runner burns 1.5 kg per lap (:221, Q11)
         const bool traced = kTrace && s >= out.trace_first && s - out.trace_first < out.trace_count;
         int tr_event = 0;
@@ -368,6 +381,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
         auto full_rank = [&](float op32) {
             set_rank(rank_by_count<NV4>(t, S_t, lane, park));
             sts_f4<0>(ra, t, op32, last, 0.0f);
+            XCHG_FENCE();
             prev = lds_f4<-16>(ra);
             have_rank = true;
         };
@@ -400,10 +414,12 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             }
             const bool drs_now = has_pred && lap > drs_until && (__fadd_rn(t, -t_pred) < 1.0f);
             if (kTrace) tr_drs = drs_now;
-            drs_f = drs_now ? drs_delta : 0.0f;
-            drs32 = drs_now ? drs32_on : 0.0f;
+            drsf = drs_now ? 1.0f : 0.0f;
             thr_sel = drs_now ? 0x7654u : 0x3210u;
-            ahead_last = has_pred ? last_pred : 0.0f;  // (retired cars: 0, never read)
+            // dirty air needs a running car ahead whose previous lap time is positive (0.0 on lap 2, Q3): both folded
+            // into the threshold the gap to the leader is compared with, so the lap itself tests `t < dthr` only
+            ahead_last = last_pred;
+            dthr = (has_pred && last_pred > 0.0f) ? dirty_thr : -kInf;
             t = __fadd_rn(t, -tl);  // (+inf stays +inf on lanes without a car)
         };
         // per-lap trace (BASELINE config 5): one 8-byte record per driver per lap, 8 n contiguous bytes per warp and lap;
@@ -419,7 +435,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                     // byte 0 position (0 = retired), 1 compound, 2 tyre age, 3 flags (bit0 retired, bit1 DRS, bit2 pitted, bits4-5 event)
                     uint32_t w0 = dnf_now ? 0x01000000u : (uint32_t)(pl + 1);
                     w0 |= (uint32_t)comp << 8;
-                    w0 |= ((uint32_t)(int)age & 0xffu) << 16;
+                    w0 |= min((uint32_t)(int)age, 255u) << 16;  // (a set can be older than 255 laps in a 300+-lap race: saturates)
                     w0 |= (tr_drs ? 0x02000000u : 0u) | (tr_pit ? 0x04000000u : 0u) | ((uint32_t)tr_event << 28);
                     if (is_car) *tr_ptr = make_uint2(w0, __float_as_uint(t));
                     tr_ptr += n;
@@ -488,11 +504,11 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             fuel = fminf(3.3f, __fadd_rn(fuel, 0.045f));
             float x = __fmaf_rn(age, eff, pc);
             x = __fadd_rn(x, -fuel);
-            x = __fadd_rn(x, -drs_f);
+            x = __fmaf_rn(drsf, ndrs_delta, x);  // == x - drs_delta with DRS, x without (one rounding either way)
             const float clean = __fmaf_rn(sigma, z, x);
             // dirty air :208-216 (gap to the LEADER, Q3); ahead_last is 0 for the leader and on lap 2
             const float held = fmaxf(__fadd_rn(clean, dirty_pen), ahead_last);
-            last = (ahead_last > 0.0f && t < dirty_thr) ? held : clean;  // (a retired car's `last` is never read)
+            last = t < dthr ? held : clean;  // (a retired car's `last` is never read)
             if (!dnf) t = __fadd_rn(t, last);
             age = __fadd_rn(age, 1.0f);  // (retired cars age on: harmless, and one predicate less)
             tba += rowb;
@@ -500,7 +516,12 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             // ---- _handle_pit_stops (:433-494) ----------------------------------------------
             const bool pit = !dnf && age > opt && rem > 5;
             if (kTrace) tr_pit = pit;
+#if MCGP_PIT_GUESS
+            const uint32_t pit_mask = __ballot_sync(FULL, pit);
+            if (pit_mask) {
+#else
             if (__any_sync(FULL, pit)) {
+#endif
                 if (pit) {
                     t = __fadd_rn(t, R.pit_loss);
                     int nc = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
@@ -516,6 +537,22 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                     tba = tb0;
                     tab.load(comp, eff, opt, pc);
                 }
+#if MCGP_PIT_GUESS
+                // A stop moves ONE car many places, which the +-2 window of window_place cannot see (it was the cause
+                // of most full recounts).  Repair the guess here, on the rare path: the stopping car's rank becomes
+                // its exact count, every car it dropped behind moves up one place.  Only a guess -- window_place
+                // still verifies the order it ends with.
+                if (have_rank) {
+                    for (uint32_t pm = pit_mask; pm; pm &= pm - 1u) {
+                        const int j = __ffs(pm) - 1;
+                        const float tj = __shfl_sync(FULL, t, j);
+                        const int rj = __shfl_sync(FULL, rank, j);
+                        const bool before = t < tj;
+                        const int cj = __popc(__ballot_sync(FULL, before));
+                        rank = lane == j ? cj : rank - ((before && rank > rj) ? 1 : 0);
+                    }
+                }
+#endif
             }
 
             // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
@@ -527,7 +564,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             const float op32 = dnf ? kNaN : __uint_as_float(pe.x);
             float thr;
             asm("prmt.b32 %0, %1, %2, %3;" : "=f"(thr) : "r"(pe.y), "r"(pe.z), "r"(thr_sel));
-            const float opb = __fadd_rn(op32, -drs32);  // as the chasing car: DRS helps (:517-518)
+            const float opb = __fmaf_rn(drsf, ndrs32, op32);  // as the chasing car: DRS helps (:517-518)
             // Re-ordering from a good guess.  `rank` holds an order in which few cars are off by more than two places
             // (last lap's order after the lap times were added: true on 4 laps of 5; a run reversal that leapfrogged a
             // neighbour): count crossings against the two neighbours on each side only, then verify (a permutation +
@@ -535,11 +572,14 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             auto window_place = [&]() {
                 const uint32_t wa = w_sh + 4u * (uint32_t)rank;
                 sts_f<0>(wa, t);
+                XCHG_FENCE();
                 const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
                 set_rank(rank + (int)moved);
+                XCHG_FENCE();  // (every lane has read its window before W / REC are rewritten)
                 sts_f4<0>(ra, t, op32, last, 0.0f);
                 const uint32_t cover = __reduce_or_sync(FULL, bit);
+                XCHG_FENCE();
                 prev = lds_f4<-16>(ra);
                 have_rank = cover == FULL && !__any_sync(FULL, !(prev.x < t));
             };
@@ -569,7 +609,9 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
                 // Verify the presumed order with one neighbour compare instead of re-counting all ranks.
                 set_rank(j + lsb(above));  // j + e - rank with e = rank + lsb(above) the run end
+                XCHG_FENCE();  // (every lane has read its run's base time before REC is rewritten)
                 sts_f4<0>(ra, t, op32, last, 0.0f);
+                XCHG_FENCE();
                 prev = lds_f4<-16>(ra);
                 have_rank = !__any_sync(FULL, !(prev.x < t));
                 if (!have_rank) window_place();  // second chance before counting all ranks
@@ -705,6 +747,8 @@ static cudaError_t launch_out(int kout, const LaunchArgs& a) {
     if (kout == 2) return launch_one<NV4, kExact, 2, kWarpsPerBlock>(a);
     return launch_one<NV4, kExact, 3, kWarpsPerBlock * MCGP_MIN_BLOCKS>(a);
 }
+
+int native_philox_rounds() { return MCGP_PHILOX_ROUNDS; }
 
 cudaError_t launch_native(const NativeRace* races_dev, const PaceEntry* pace_dev, int pace_rows, int pace_stride, int n_races,
                           int max_n, unsigned long long n_sims, unsigned long long sim_begin, unsigned long long seed, bool exact,

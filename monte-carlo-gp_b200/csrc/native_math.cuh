@@ -4,11 +4,20 @@
 
 namespace mcgp {
 
-// Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
+// Philox4x32-R (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
 // key = (seed_lo, seed_hi); counter = (sim_lo, sim_hi, lap<<8 | lane, race stream).
-// The ten round keys depend only on the seed, so the host expands them once and passes them as a kernel
+// R = MCGP_PHILOX_ROUNDS = 7: the paper's Table 2 lists Philox4x32-7 as the fastest variant that is Crush-resistant
+// (passes SmallCrush, Crush and BigCrush); 10 is its conservative default.  A race consumes one call per lane per lap
+// PAIR and the call is the largest single item of the lap budget (26 of 190 executed instructions per race-lap at
+// R = 10), so the three safety-margin rounds are spent elsewhere; -DMCGP_PHILOX_ROUNDS=10 restores them.  The scalar
+// mirror (oracle/native_mirror.c: MIRROR_PHILOX_ROUNDS) must use the same R; both are pinned to the Random123
+// known-answer vectors for R = 7 and R = 10 (tests/test_native_mirror.py).
+// The round keys depend only on the seed, so the host expands them once and passes them as a kernel
 // parameter: they sit in the constant bank and feed the round's 3-input XOR (LOP3) as immediate-like operands
 // instead of costing two uniform adds per round per call.
+#ifndef MCGP_PHILOX_ROUNDS
+#define MCGP_PHILOX_ROUNDS 7
+#endif
 struct PhiloxKeys {
     uint32_t k0[10], k1[10];
 };
@@ -25,7 +34,7 @@ __host__ __device__ inline PhiloxKeys philox_expand_key(uint32_t seed_lo, uint32
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& key) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < MCGP_PHILOX_ROUNDS; r++) {
         const uint64_t p0 = (uint64_t)M0 * c0;
         const uint64_t p1 = (uint64_t)M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r];

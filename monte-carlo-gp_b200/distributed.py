@@ -64,7 +64,10 @@ class ShardedSimulator:
         self.torch = torch
         self.device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
         torch.cuda.set_device(self.device)
-        self.engine = capi.get_engine(self.device)
+        # An engine of its own: the resident race blocks and claim counters must not be the ones RaceSimulator's
+        # host-buffer calls (capi.get_engine) re-upload on every call.  Launches of one engine are ordered by the
+        # library whatever stream they are given (include/mcgp.h), so overlapping launches cannot share counters.
+        self.engine = capi.Engine(self.device)
         self.engine.upload_races(races)
         self.n_races, self.n = self.engine.n_races, self.engine.n_drivers
         self.flags = flags

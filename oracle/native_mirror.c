@@ -1,10 +1,10 @@
-/* TEST INFRASTRUCTURE -- scalar CPU mirror of the NATIVE-mode kernel (Philox4x32-10 draws, FP32 state).
+/* TEST INFRASTRUCTURE -- scalar CPU mirror of the NATIVE-mode kernel (Philox4x32-7 draws, FP32 state).
  *
  * The native kernel cannot be compared with the reference draw by draw (different RNG), only
  * statistically.  To still check its *logic* exactly, this file restates the native algorithm the plain
  * way -- one car at a time, full sorts, no warp tricks -- following the reference's structure
  * (src/simulation.py:102-560, cited per function) with the native arithmetic:
- *   - draws: Philox4x32-10, key = seed, counter = (sim, lap<<8 | lane, stream)
+ *   - draws: Philox4x32-R (R = MIRROR_PHILOX_ROUNDS = 7, as the kernel), key = seed, counter = (sim, lap<<8 | lane, stream)
  *       lap 0  word0 of lane p          -> grid position p's uniform
  *       lap 1  word0 lap-1 DNF; words 1,2 -> Box-Muller pair (cos: pace noise, sin: start delta);
  *              word3 (top 23 bits) -> the retirement lap >= 2, geometric: 2 + floor(ln u / ln(1 - rate))
@@ -28,8 +28,13 @@
 
 typedef struct { uint32_t x, y, z, w; } u4;
 
-static u4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-    for (int r = 0; r < 10; r++) {
+/* must equal MCGP_PHILOX_ROUNDS of monte-carlo-gp_b200/csrc/native_math.cuh (checked by tests/test_native_mirror.py) */
+#ifndef MIRROR_PHILOX_ROUNDS
+#define MIRROR_PHILOX_ROUNDS 7
+#endif
+
+static u4 philox_r(int rounds, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
@@ -37,6 +42,15 @@ static u4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0
     }
     u4 o = {c0, c1, c2, c3};
     return o;
+}
+static u4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox_r(MIRROR_PHILOX_ROUNDS, c0, c1, c2, c3, k0, k1);
+}
+int orc_native_philox_rounds(void) { return MIRROR_PHILOX_ROUNDS; }
+/* Philox4x32-`rounds` on one counter block: exported for the Random123 known-answer vectors */
+void orc_philox4x32(int rounds, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    const u4 o = philox_r(rounds, ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
 }
 
 static float as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
@@ -263,7 +277,7 @@ static void emit_trace(trace_rec* trace, int64_t s, int L, int n, int lap, const
         trace_rec* r = &trace[((s * L) + (lap - 1)) * n + d];
         r->position = cars[d].dnf ? 0 : (uint8_t)(cars[d].pos_live + 1);
         r->compound = (uint8_t)cars[d].comp;
-        r->tire_age = (uint8_t)(int)cars[d].age;
+        r->tire_age = (uint8_t)((int)cars[d].age > 255 ? 255 : (int)cars[d].age);
         r->flags = (uint8_t)((cars[d].dnf ? 1 : 0) | (cars[d].drs ? 2 : 0) | (pitted[d] ? 4 : 0) | ((ev > 3 ? 3 : ev) << 4));
         r->gap = cars[d].t;
     }
@@ -303,7 +317,8 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
                 if (total > 0.0f) {
                     const float target = u * total;
                     for (int i = 0; i < n && sel < 0; i++) if (remaining[i] && pr[i] > 0.0f && c[i] > target) sel = i;
-                    if (sel < 0) for (int i = 0; i < n; i++) if (remaining[i]) sel = i;
+                    /* u * total rounded up to total: the last remaining driver that has probability mass */
+                    if (sel < 0) for (int i = 0; i < n; i++) if (remaining[i] && pr[i] > 0.0f) sel = i;
                 } else {
                     int nrem = 0;
                     for (int i = 0; i < n; i++) nrem += remaining[i];

@@ -19,6 +19,11 @@ int orc_run_native(const orc_params* p, uint64_t seed, uint32_t stream, uint64_t
  * (mcgp_pace_table): the two are written independently and must agree bit for bit. */
 int orc_native_op32_table(const orc_params* p, float* out);
 
+/* Philox rounds the mirror was built with (must equal the kernel's MCGP_PHILOX_ROUNDS), and the bare block function
+ * for the Random123 known-answer vectors. */
+int orc_native_philox_rounds(void);
+void orc_philox4x32(int rounds, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
 #ifdef __cplusplus
 }
 #endif

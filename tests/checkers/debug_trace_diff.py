@@ -1,7 +1,7 @@
 """Debug helper (GPU box): first per-lap trace record where the native kernel and the CPU mirror differ."""
 import sys, os
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import golden_cases as gc
 import mcgp_b200 as mcgp

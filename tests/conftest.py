@@ -14,6 +14,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: longer statistical checks")
 
 
+def _gpu_visible() -> bool:
+    """A CUDA device node is present.  Deliberately NOT "the library loads": on a GPU box a missing or broken
+    libmcgp.so must make the gpu tests FAIL (there is no CPU fallback to fall back to), not skip."""
+    return any(os.path.exists(f"/dev/nvidia{i}") for i in range(16))
+
+
+def pytest_collection_modifyitems(config, items):
+    if _gpu_visible():
+        return
+    skip = pytest.mark.skip(reason="needs a B200: no /dev/nvidia* device on this machine (run with -m gpu on the GPU box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 

@@ -43,3 +43,36 @@ def test_native_draw_plan_is_uniform(oracle):
     # position p (0-based) is taken by a retired car iff at least 20-p cars retired; count retirements via times<0
     retired = (out["times"] < 0).sum(1)
     assert abs(retired.mean() - expect_dnf_per_race) < 4 * np.sqrt(expect_dnf_per_race / n)
+
+
+# Random123's known-answer vectors (kat_vectors, philox4x32 with 7 and 10 rounds): counter, key -> output
+_PHILOX_KAT = [
+    (7, [0, 0, 0, 0], [0, 0], [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]),
+    (7, [0xffffffff] * 4, [0xffffffff] * 2, [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]),
+    (7, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]),
+    (10, [0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    (10, [0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+    (10, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+]
+
+
+def test_philox_known_answers(oracle):
+    """The mirror's block function is Philox4x32-R as published (the kernel is held bit-exact to the mirror)."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_philox4x32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_philox4x32.restype = None
+    for rounds, ctr, key, want in _PHILOX_KAT:
+        c, k, o = np.array(ctr, np.uint32), np.array(key, np.uint32), np.zeros(4, np.uint32)
+        L.orc_philox4x32(rounds, c.ctypes.data, k.ctypes.data, o.ctypes.data)
+        assert o.tolist() == want, (rounds, [hex(x) for x in o])
+
+
+def test_mirror_and_kernel_use_the_same_round_count(oracle):
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "monte-carlo-gp_b200", "csrc", "native_math.cuh")).read()
+    kernel_rounds = int(re.search(r"#define MCGP_PHILOX_ROUNDS (\d+)", src).group(1))
+    L = oracle.lib()
+    assert L.orc_native_philox_rounds() == kernel_rounds == 7
