@@ -44,11 +44,19 @@ struct NativeRace {
 // as its float: the decision is monotone in P_ahead, so on the GPU it is ONE float compare, f(P_ahead) >= thr,
 // bit-identical to the FP64 decision; the same floats feed the (continuous) overtake probability.
 // Layout: entry[age][lane], `stride` lanes per row, rows = total_laps + 5 (a tyre set is at most 4 + laps old).
-struct PaceEntry {
+struct PaceEntry {  // host-side / mcgp_pace_table form
     float op32;     // f(P[d][age])
     float thr0;     // this car chasing WITHOUT DRS may attack iff op32_ahead >= thr0 (+inf: never)
     float thr1;     // ... with DRS
     uint32_t _pad;
+};
+// Device form: pairs[drs][age][lane] -- two dense tables of 8-byte entries {op32, thr}, the first for a car without
+// DRS, the second with, followed by MCGP_LANES entries of padding (lanes without a car read past their row).  A lane
+// reads ONE 8-byte entry per lap at `age row + lane` of the table its DRS state selects: a contiguous 160 bytes per
+// warp when the cars' tyres are equally old, i.e. 2 shared-memory wavefronts where the 16-byte entries of round 1
+// needed 4-5 (the LSU data pipe was as busy as the issue port).
+struct PacePair {
+    float op32, thr;
 };
 
 // ---- replay mode (FP64, bit-exact) -----------------------------------------------------------

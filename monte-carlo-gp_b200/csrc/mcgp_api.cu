@@ -14,7 +14,7 @@
 #include "device_params.h"
 
 namespace mcgp {
-cudaError_t launch_native(const NativeRace* races_dev, const PaceEntry* pace_dev, int pace_rows, int pace_stride, int n_races,
+cudaError_t launch_native(const NativeRace* races_dev, const PacePair* pace_dev, int pace_rows, int pace_stride, int n_races,
                           int max_n, unsigned long long n_sims,
                           unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
@@ -25,6 +25,7 @@ cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
                           unsigned long long* work_counter, int sm_count, cudaStream_t st);
 int native_philox_rounds();
+size_t pace_pairs_per_race(int rows, int stride);  // device form of one race's overtake pace tables (device_params.h: PacePair)
 }  // namespace mcgp
 
 struct mcgp_context {
@@ -33,7 +34,7 @@ struct mcgp_context {
     int cc_major = 0, cc_minor = 0;
     std::string err;
     NativeRace* native_dev = nullptr;
-    PaceEntry* pace_dev = nullptr;     // [race][pace_rows][pace_stride] overtake pace tables
+    PacePair* pace_dev = nullptr;      // [race][drs][pace_rows][pace_stride] overtake pace tables (+ padding per race)
     int pace_rows = 0, pace_stride = 0;
     int cap_races = 0;                 // allocated capacity of native_dev / replay_dev / work_counter (races)
     size_t cap_pace = 0;               // allocated capacity of pace_dev (entries)
@@ -320,8 +321,8 @@ static int upload_native(mcgp_handle h, const mcgp_race_params* races, int n_rac
         uniform = uniform && races[r].total_laps == races[0].total_laps;
     }
     const int stride = races[0].n_drivers <= 20 ? 20 : MCGP_LANES;
-    const size_t per_race = (size_t)rows * stride;
-    const size_t b_nat = sizeof(NativeRace) * (size_t)n_races, b_pace = sizeof(PaceEntry) * per_race * n_races;
+    const size_t per_race = mcgp::pace_pairs_per_race(rows, stride);
+    const size_t b_nat = sizeof(NativeRace) * (size_t)n_races, b_pace = sizeof(PacePair) * per_race * n_races;
     wait_last_launch(h);  // in-flight kernels still read the old blocks
     drop_resident(h);
     // host staging: pinned (async path) or a plain temporary
@@ -338,10 +339,18 @@ static int upload_native(mcgp_handle h, const mcgp_race_params* races, int n_rac
         stage = tmp.data();
     }
     NativeRace* nat = reinterpret_cast<NativeRace*>(stage);
-    PaceEntry* pace = reinterpret_cast<PaceEntry*>(stage + b_nat);
+    PacePair* pace = reinterpret_cast<PacePair*>(stage + b_nat);
+    std::vector<PaceEntry> entries;
+    try { entries.resize((size_t)rows * stride); } catch (...) { return fail(h, MCGP_ENOMEM, "out of host memory"); }
+    memset(pace, 0, b_pace);
     for (int r = 0; r < n_races; r++) {
         derive_native(&races[r], &nat[r]);
-        build_pace_table(&races[r], rows, stride, pace + per_race * r);
+        build_pace_table(&races[r], rows, stride, entries.data());
+        PacePair* t0 = pace + per_race * r, *t1 = t0 + entries.size();  // without / with DRS
+        for (size_t i = 0; i < entries.size(); i++) {
+            t0[i] = PacePair{entries[i].op32, entries[i].thr0};
+            t1[i] = PacePair{entries[i].op32, entries[i].thr1};
+        }
     }
     // device blocks are grow-only: a product-sized call (10 000 sims = 0.13 ms of kernel) must not pay for cudaMalloc / cudaFree
     cudaError_t e = cudaSuccess;
@@ -534,7 +543,7 @@ int mcgp_launch_native_laphist(mcgp_handle h, uint64_t n_sims, uint64_t sim_begi
     if (h && !laphist_dev) return fail(h, MCGP_EINVAL, "laphist_dev is NULL");
     if (h && h->native_dev && h->n_races > 0) {
         const size_t cells = (size_t)(h->pace_rows - 5) * h->n_drivers * h->n_drivers;
-        const size_t smem = ((size_t)h->pace_rows * h->pace_stride + MCGP_LANES) * sizeof(PaceEntry) + cells * 4;
+        const size_t smem = mcgp::pace_pairs_per_race(h->pace_rows, h->pace_stride) * sizeof(PacePair) + cells * 4;
         if (smem > 180u * 1024u)
             return fail(h, MCGP_EINVAL, "laps x drivers^2 too large: the lap histogram (4 B per cell) and the pace table must fit 180 KB of shared memory");
     }
@@ -613,7 +622,7 @@ int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, u
     if (times_host && (rc = scratch_get(h, 6, tim_bytes, &tim_dev))) return rc;
     // the count table travels through the pinned block BEHIND the parameter staging area (which the async upload of
     // this very call may still be reading)
-    const size_t stage_off = (sizeof(NativeRace) * (size_t)n_races + sizeof(PaceEntry) * (size_t)h->pace_rows * h->pace_stride * n_races + 4095) & ~(size_t)4095;
+    const size_t stage_off = (sizeof(NativeRace) * (size_t)n_races + sizeof(PacePair) * mcgp::pace_pairs_per_race(h->pace_rows, h->pace_stride) * n_races + 4095) & ~(size_t)4095;
     void* pin = nullptr;
     if (h->pinned_sz < stage_off + hist_bytes) {
         // growing the block would free memory an in-flight copy reads: finish the upload first

@@ -45,9 +45,7 @@ namespace mcgp {
 #ifndef MCGP_WARPS_PER_BLOCK
 #define MCGP_WARPS_PER_BLOCK 8
 #endif
-#ifndef MCGP_PIT_GUESS
-#define MCGP_PIT_GUESS 1  // pit stops repair the rank guess (see run_lap); 0 = the round-1 behaviour
-#endif
+
 constexpr int kWarpsPerBlock = MCGP_WARPS_PER_BLOCK;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned FULL = 0xffffffffu;
@@ -60,14 +58,15 @@ constexpr uint32_t kVscRoll16 = 19660u;  // floor(0.3 * 2^16)
 // (a NOP), not a WARPSYNC.  An empty asm with a memory clobber is NOT enough: ptxas reorders a thread's LDS above
 // its own STS to a different address.
 #define WARP_FENCE() __syncwarp()
-// -DMCGP_STRICT_FENCES: additionally put a __syncwarp() between every shared-memory store and the cross-lane load that
-// follows it in the record / window exchanges (XCHG_FENCE below).  The default build relies on the volatile accessors
-// instead (in-order LDS/STS issue of a convergent warp); the strict build is the memory-model-clean variant the
-// GPU tests hold the default build against, bit for bit (tests/test_gpu_native.py::test_strict_fence_build_is_identical).
-#ifdef MCGP_STRICT_FENCES
-#define XCHG_FENCE() __syncwarp()
-#else
+// XCHG_FENCE: the ordering point between a lane's store into a rank-indexed exchange array (records, window) and the
+// loads of OTHER lanes' slots that follow, and between such loads and the next rewrite of the array.  Round 1 relied
+// on the volatile accessors alone (a convergent warp issues its LDS / STS in program order); the CUDA memory model
+// does not promise that, so the fence is spelled out.  Measured cost: 0.7 % (83.3 -> 82.7 M races/s, r2a A/B);
+// -DMCGP_RELAXED_FENCES rebuilds the round-1 behaviour for comparison.
+#ifdef MCGP_RELAXED_FENCES
 #define XCHG_FENCE() ((void)0)
+#else
+#define XCHG_FENCE() __syncwarp()
 #endif
 
 // Shared-memory accessors on 32-bit shared addresses.  `volatile` keeps ptxas from reordering a lane's LDS above
@@ -96,9 +95,20 @@ __device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, fl
     asm volatile("st.volatile.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
-__device__ __forceinline__ uint4 lds_u4(uint32_t a) {  // read-only data: no ordering needed
-    uint4 v;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+template <int OFF>
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f2(uint32_t a, float x, float y) {
+    asm volatile("st.volatile.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(x), "f"(y) : "memory");
+}
+
+__device__ __forceinline__ float2 lds_pair(uint32_t a) {  // read-only data: no ordering needed
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
     return v;
 }
 
@@ -178,7 +188,7 @@ struct NativeOutputs {
 // per SM where the others run four blocks of eight.
 template <int NV4, bool kExact, int kOut, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, (MCGP_MIN_BLOCKS * MCGP_WARPS_PER_BLOCK) / kWarps)
-native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict__ ptab, const int pt_rows, const int pt_stride,
+native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict__ ptab, const int pt_rows, const int pt_stride,  // ptab: PacePair tables, two pairs per uint4
                    unsigned long long n_sims, unsigned long long sim_begin,
                    const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
                    const __grid_constant__ NativeOutputs out, unsigned long long* __restrict__ work_counter) {
@@ -188,11 +198,15 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     uint8_t* __restrict__ finish = out.finish;
     float* __restrict__ times = out.times;
     __shared__ NativeRace R;
-    extern __shared__ __align__(16) uint4 PT[];  // overtake pace table [age][lane] (device_params.h: PaceEntry) + one row of padding
+    extern __shared__ __align__(16) uint4 PT[];  // overtake pace tables [drs][age][lane] of 8-byte pairs (device_params.h: PacePair) + padding
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     __shared__ __align__(16) float S_t_all[kWarps][32];
     __shared__ float S_w_all[kWarps][48];              // window scratch: times by OLD rank, -inf / +inf pads
-    __shared__ __align__(16) float4 S_rec_all[kWarps][36];  // records by rank: {time, overtake pace, last lap, lane}
+    // Records by rank: {time, overtake pace (NaN = retired)}, 8 bytes.  A rank-indexed access is a random permutation over the
+    // banks; as 16-byte records (round 1: + last lap, padding) each exchange cost 8-10 shared-memory wavefronts instead of
+    // the 4 a contiguous access needs, and the LSU data pipe ran at 77 % of its peak -- as busy as the issue port (ncu r2a).
+    // The last lap of the car ahead is only needed once per lap, so it travels through the window scratch instead.
+    __shared__ __align__(16) float2 S_rec_all[kWarps][36];
 
     // A block starts on race blockIdx.y of the batch and, when that race's sims are all claimed, hops to the next
     // race that still has work (a season batch mixes 44- and 78-lap races: without hopping the blocks of the short
@@ -211,11 +225,11 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
         uint32_t* dst = reinterpret_cast<uint32_t*>(&R);
         for (int i = threadIdx.x; i < (int)(sizeof(NativeRace) / 4); i += kThr) dst[i] = src[i];
         for (int i = threadIdx.x; i < MCGP_LANES * MCGP_LANES; i += kThr) hist_s[i] = 0;
-        const int pt_n = pt_rows * pt_stride;
+        const int pt_n = pt_rows * pt_stride + MCGP_LANES / 2;  // uint4 words = pairs of entries: 2 tables + padding
         const uint4* psrc = ptab + (size_t)race * pt_n;
-        for (int i = threadIdx.x; i < pt_n + MCGP_LANES; i += kThr) PT[i] = i < pt_n ? psrc[i] : make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < pt_n; i += kThr) PT[i] = psrc[i];
         if (kLapHist) {
-            uint32_t* lh = reinterpret_cast<uint32_t*>(PT + pt_n + MCGP_LANES);
+            uint32_t* lh = reinterpret_cast<uint32_t*>(PT + pt_n);
             for (int i = threadIdx.x; i < out.lh_cells; i += kThr) lh[i] = 0u;
         }
     }
@@ -229,10 +243,10 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     const float kInf = __int_as_float(0x7f800000), kNaN = __int_as_float(0x7fc00000);
     float* S_t = S_t_all[warp];
     float* W = S_w_all[warp] + 8;   // W[-8..-1] = -inf, W[0..32) = times by rank, W[32..40) = +inf: no index guards needed
-    float4* REC = S_rec_all[warp] + 2;  // REC[-1] = {-inf, NaN, 0, -}: "no car ahead" blocks the pair and ends the order check
+    float2* REC = S_rec_all[warp] + 2;  // REC[-1] = {-inf, NaN}: "no car ahead" blocks the pair and ends the order check
     W[lane - 8] = lane < 8 ? -kInf : kInf;
     if (lane < 16) W[lane + 24] = kInf;
-    if (lane < 2) REC[lane - 2] = make_float4(-kInf, kNaN, 0.0f, 0.0f);
+    if (lane < 2) REC[lane - 2] = make_float2(-kInf, kNaN);
     __syncwarp();
     const uint32_t w_sh = smem_u32(W), rec_sh = smem_u32(REC);
     uint32_t grid_sh = smem_u32(&R.grid[0][lane]);
@@ -248,9 +262,10 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     const float sigma = R.sigma[lane];
     // this lane's column of the pace table: entry [age][lane] sits at tb0 + age * rowb (lanes without a car read
     // a neighbouring entry or the padding row; they are retired from lap 0, so nothing of it is used)
-    uint32_t tb0 = smem_u32(PT) + 16u * (uint32_t)lane;
+    uint32_t tb0 = smem_u32(PT) + 8u * (uint32_t)lane;
     asm volatile("" : "+r"(tb0));  // (kept in a register, like grid_sh)
-    const uint32_t rowb = 16u * (uint32_t)__shfl_sync(FULL, pt_stride, 0);
+    const uint32_t rowb = 8u * (uint32_t)__shfl_sync(FULL, pt_stride, 0);
+    const uint32_t tsel_on = rowb * (uint32_t)__shfl_sync(FULL, pt_rows, 0);  // byte offset of the with-DRS table
     // (values needed once per race or only on rare paths -- retirement law, pit loss, red / SC thresholds -- are read
     // from the shared parameter block where they are used: the hot loop has no register to spare for them)
     const float ndrs_delta = -R.drs_delta;
@@ -362,10 +377,10 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
         int rank;
         uint32_t bit;          // 1 << rank
         uint32_t ra;           // shared address of REC[rank]
-        float4 prev;           // record of the car one rank ahead (REC[rank - 1]), valid whenever have_rank
+        float2 prev;           // record of the car one rank ahead (REC[rank - 1]), valid whenever have_rank
         bool have_rank;        // warp-uniform: rank / bit / wa / ra / prev / REC describe the current times
         float drsf = 0.0f;                 // 1.0f while DRS is enabled for this car, else 0.0f: fma(drsf, -delta, x) == x - delta / x
-        uint32_t thr_sel = 0x3210u;        // PRMT selector: the no-DRS (first operand) or the DRS (second operand) threshold
+        uint32_t tsel = 0u;                // byte offset of the pace table this car reads: 0 without DRS, tsel_on with
         float dthr = -kInf;                // dirty_thr while a car with a positive last lap runs ahead, else -inf (:208-216)
         float fuel = 0.0f;     // (110 - fuel_load) * 0.03 of the current lap: every runner burns 1.5 kg per lap (:221, Q11)
         const bool traced = kTrace && s >= out.trace_first && s - out.trace_first < out.trace_count;
@@ -375,14 +390,14 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
         auto set_rank = [&](int r) {
             rank = r;
             bit = 1u << (r & 31);
-            ra = rec_sh + 16u * (uint32_t)r;
+            ra = rec_sh + 8u * (uint32_t)r;
         };
         // all-cars rank by counting, then publish the records
         auto full_rank = [&](float op32) {
             set_rank(rank_by_count<NV4>(t, S_t, lane, park));
-            sts_f4<0>(ra, t, op32, last, 0.0f);
+            sts_f2<0>(ra, t, op32);
             XCHG_FENCE();
-            prev = lds_f4<-16>(ra);
+            prev = lds_f2<-8>(ra);
             have_rank = true;
         };
         // live cars' rank among the runners, derived on demand from the all-cars rank (events, classification)
@@ -398,24 +413,30 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             const bool pd = prev.y != prev.y;
             const uint32_t B = __ballot_sync(FULL, live && pd);
             bool has_pred = live && !pd;
-            float tl, t_pred = prev.x, last_pred = prev.z;
+            // last lap times by rank, through the window scratch (window_place rewrites every slot before it reads)
+            const uint32_t wl = w_sh + 4u * (uint32_t)rank;
+            sts_f<0>(wl, last);
+            XCHG_FENCE();
+            float tl, t_pred = prev.x, last_pred = lds_f<-4>(wl);  // (rank 0 reads the -inf pad: no car ahead)
             if (__popc(B) == 1) {
                 tl = __shfl_sync(FULL, t, msb(B));
             } else if (B) {  // retired cars sit between runners (the lap of a retirement): search the live mask
                 const uint32_t LM = __reduce_or_sync(FULL, live ? bit : 0u);
-                tl = lds_f<0>(rec_sh + 16u * (uint32_t)(__ffs(LM) - 1));
+                tl = lds_f<0>(rec_sh + 8u * (uint32_t)(__ffs(LM) - 1));
                 const uint32_t below = live ? (LM & (bit - 1u)) : 0u;
                 has_pred = below != 0u;
-                const float4 pr = lds_f4<0>(rec_sh + 16u * (uint32_t)(has_pred ? 31 - __clz(below) : 0));
-                t_pred = pr.x;
-                last_pred = pr.z;
+                const int rp = has_pred ? 31 - __clz(below) : 0;
+                t_pred = lds_f<0>(rec_sh + 8u * (uint32_t)rp);
+                last_pred = lds_f<0>(w_sh + 4u * (uint32_t)rp);
             } else {  // nobody left running: times stay as they are
+                XCHG_FENCE();
                 return;
             }
+            XCHG_FENCE();  // (the scratch is rewritten by the next lap's window_place)
             const bool drs_now = has_pred && lap > drs_until && (__fadd_rn(t, -t_pred) < 1.0f);
             if (kTrace) tr_drs = drs_now;
             drsf = drs_now ? 1.0f : 0.0f;
-            thr_sel = drs_now ? 0x7654u : 0x3210u;
+            tsel = drs_now ? tsel_on : 0u;
             // dirty air needs a running car ahead whose previous lap time is positive (0.0 on lap 2, Q3): both folded
             // into the threshold the gap to the leader is compared with, so the lap itself tests `t < dthr` only
             ahead_last = last_pred;
@@ -449,7 +470,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
         auto count_lap = [&](const int lap, const bool dnf_now) {
             if (kLapHist) {
                 const int pl = live_position(!dnf_now);
-                uint32_t* lh = reinterpret_cast<uint32_t*>(PT + pt_rows * pt_stride + MCGP_LANES);
+                uint32_t* lh = reinterpret_cast<uint32_t*>(PT + pt_rows * pt_stride + MCGP_LANES / 2);
                 if (is_car && !dnf_now) atomicAdd(&lh[((lap - 1) * n + lane) * n + pl], 1u);
             }
         };
@@ -516,12 +537,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             // ---- _handle_pit_stops (:433-494) ----------------------------------------------
             const bool pit = !dnf && age > opt && rem > 5;
             if (kTrace) tr_pit = pit;
-#if MCGP_PIT_GUESS
-            const uint32_t pit_mask = __ballot_sync(FULL, pit);
-            if (pit_mask) {
-#else
             if (__any_sync(FULL, pit)) {
-#endif
                 if (pit) {
                     t = __fadd_rn(t, R.pit_loss);
                     int nc = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
@@ -537,22 +553,6 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                     tba = tb0;
                     tab.load(comp, eff, opt, pc);
                 }
-#if MCGP_PIT_GUESS
-                // A stop moves ONE car many places, which the +-2 window of window_place cannot see (it was the cause
-                // of most full recounts).  Repair the guess here, on the rare path: the stopping car's rank becomes
-                // its exact count, every car it dropped behind moves up one place.  Only a guess -- window_place
-                // still verifies the order it ends with.
-                if (have_rank) {
-                    for (uint32_t pm = pit_mask; pm; pm &= pm - 1u) {
-                        const int j = __ffs(pm) - 1;
-                        const float tj = __shfl_sync(FULL, t, j);
-                        const int rj = __shfl_sync(FULL, rank, j);
-                        const bool before = t < tj;
-                        const int cj = __popc(__ballot_sync(FULL, before));
-                        rank = lane == j ? cj : rank - ((before && rank > rj) ? 1 : 0);
-                    }
-                }
-#endif
             }
 
             // ---- _simulate_overtakes (:496-536): <= 3 passes in rank space ------------------
@@ -560,10 +560,9 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             // The pair test `pace_delta > overtake_delta` (:514-521) is decided in FP64 on the host for every reachable
             // (driver, tyre age, DRS) and tabulated (device_params.h: PaceEntry): this car, chasing, may attack the car
             // ahead iff op32_ahead >= thr -- one float compare that reproduces the FP64 decision bit for bit.
-            const uint4 pe = lds_u4(tba);
-            const float op32 = dnf ? kNaN : __uint_as_float(pe.x);
-            float thr;
-            asm("prmt.b32 %0, %1, %2, %3;" : "=f"(thr) : "r"(pe.y), "r"(pe.z), "r"(thr_sel));
+            const float2 pe = lds_pair(tba + tsel);
+            const float op32 = dnf ? kNaN : pe.x;
+            const float thr = pe.y;
             const float opb = __fmaf_rn(drsf, ndrs32, op32);  // as the chasing car: DRS helps (:517-518)
             // Re-ordering from a good guess.  `rank` holds an order in which few cars are off by more than two places
             // (last lap's order after the lap times were added: true on 4 laps of 5; a run reversal that leapfrogged a
@@ -577,10 +576,10 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
                 set_rank(rank + (int)moved);
                 XCHG_FENCE();  // (every lane has read its window before W / REC are rewritten)
-                sts_f4<0>(ra, t, op32, last, 0.0f);
+                sts_f2<0>(ra, t, op32);
                 const uint32_t cover = __reduce_or_sync(FULL, bit);
                 XCHG_FENCE();
-                prev = lds_f4<-16>(ra);
+                prev = lds_f2<-8>(ra);
                 have_rank = cover == FULL && !__any_sync(FULL, !(prev.x < t));
             };
             window_place();  // first ordering of the lap
@@ -603,16 +602,16 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 const int j = msb(clear_below);  // run start (bit 0 of M is never set)
                 const uint32_t above = ~((M >> rank) >> 1);  // bit i clear <=> pair (rank+i, rank+i+1) swapped
                 const int sn = (int)(~above & 1u);
-                const float base = lds_f<0>(rec_sh + 16u * (uint32_t)j);
+                const float base = lds_f<0>(rec_sh + 8u * (uint32_t)j);
                 t = __fmaf_rn(-0.1f, (float)(rank - j - 2 * sn), base);  // (k = sn = 0: base is the car's own time)
                 // The new order is almost always the old one with every run [j, e] reversed (the re-written times
                 // descend by 0.1 s inside a run); only a run that leapfrogs a neighbour outside it breaks that.
                 // Verify the presumed order with one neighbour compare instead of re-counting all ranks.
                 set_rank(j + lsb(above));  // j + e - rank with e = rank + lsb(above) the run end
                 XCHG_FENCE();  // (every lane has read its run's base time before REC is rewritten)
-                sts_f4<0>(ra, t, op32, last, 0.0f);
+                sts_f2<0>(ra, t, op32);
                 XCHG_FENCE();
-                prev = lds_f4<-16>(ra);
+                prev = lds_f2<-8>(ra);
                 have_rank = !__any_sync(FULL, !(prev.x < t));
                 if (!have_rank) window_place();  // second chance before counting all ranks
                 return true;
@@ -689,7 +688,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
         if (v) atomicAdd(&hist[(unsigned long long)race * n * n + i], (unsigned long long)v);
     }
     if (kLapHist) {
-        const uint32_t* lh = reinterpret_cast<const uint32_t*>(PT + pt_rows * pt_stride + MCGP_LANES);
+        const uint32_t* lh = reinterpret_cast<const uint32_t*>(PT + pt_rows * pt_stride + MCGP_LANES / 2);
         for (int i = threadIdx.x; i < out.lh_cells; i += kThr) {
             const uint32_t v = lh[i];
             if (v) atomicAdd(&out.laphist[(unsigned long long)race * out.lh_cells + i], (unsigned long long)v);
@@ -749,13 +748,14 @@ static cudaError_t launch_out(int kout, const LaunchArgs& a) {
 }
 
 int native_philox_rounds() { return MCGP_PHILOX_ROUNDS; }
+size_t pace_pairs_per_race(int rows, int stride) { return 2 * (size_t)rows * stride + MCGP_LANES; }
 
-cudaError_t launch_native(const NativeRace* races_dev, const PaceEntry* pace_dev, int pace_rows, int pace_stride, int n_races,
+cudaError_t launch_native(const NativeRace* races_dev, const PacePair* pace_dev, int pace_rows, int pace_stride, int n_races,
                           int max_n, unsigned long long n_sims, unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
                           unsigned long long trace_first, unsigned long long trace_count, unsigned long long* laphist,
                           unsigned long long* work_counter, int sm_count, cudaStream_t st) {
-    static_assert(sizeof(PaceEntry) == sizeof(uint4), "pace table entries are staged as 16-byte words");
+    static_assert(2 * sizeof(PacePair) == sizeof(uint4), "pace table entries are staged two to a 16-byte word");
     const int kout = laphist ? 3 : trace ? 2 : (finish != nullptr || times != nullptr) ? 1 : 0;
     LaunchArgs a;
     a.races = races_dev; a.ptab = reinterpret_cast<const uint4*>(pace_dev); a.pt_rows = pace_rows; a.pt_stride = pace_stride;
@@ -765,7 +765,7 @@ cudaError_t launch_native(const NativeRace* races_dev, const PaceEntry* pace_dev
     const int lh_cells = laphist ? (pace_rows - 5) * max_n * max_n : 0;  // laps of the longest race x n x n
     a.out = NativeOutputs{finish, times, trace, trace_first, trace ? trace_count : 0ull, laphist, lh_cells};
     a.wc = work_counter; a.n_races = n_races; a.sm_count = sm_count; a.st = st;
-    a.dyn_smem = ((size_t)pace_rows * pace_stride + MCGP_LANES) * sizeof(uint4)  // + one padding row (lanes without a car)
+    a.dyn_smem = pace_pairs_per_race(pace_rows, pace_stride) * sizeof(PacePair)  // both tables + padding (lanes without a car)
                  + (size_t)lh_cells * sizeof(uint32_t);
     if (max_n <= 20) return exact ? launch_out<5, true>(kout, a) : launch_out<5, false>(kout, a);
     return exact ? launch_out<8, true>(kout, a) : launch_out<8, false>(kout, a);
