@@ -33,14 +33,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W_RACE = {57: 17100, 78: 23190}  # algorithmic warp-instructions per race, SURVEY.md §8(d)
-# From the committed ncu capture of this kernel build (profiles/, `ncu --set full`, 2 M races, one launch):
-NCU = {"capture": "profiles/r1s_native_kernel_ncu_raw.csv", "executed_warp_instr_per_race": 10865.9,
-       # dram__bytes_read.sum + dram__bytes_write.sum of that launch: 13.6 MB + 48.0 MB, i.e. write-back of the 256 MiB
-       # L2-flush fill that precedes it; the kernel's own input is 27 KB per block out of L2 (captures whose launch
-       # is not preceded by a fill show 0.06-0.2 MB: profiles/r1m, r1q)
-       "dram_bytes_per_launch": 61560576}
+# The ncu figures of the headline kernel come from the committed summary of its capture (tools/ncu_summary.py writes
+# it together with the SHA-256 of the kernel sources); nothing from a profiler is hard-coded here, and the line says
+# whether the capture belongs to the build that ran (roofline.capture_matches_build).
+NCU_SUMMARY = os.path.join("profiles", "r2_native_ncu_summary.json")
+PYTHON_REFERENCE = os.path.join("profiles", "r2_python_reference.json")
+KERNEL_SOURCES = ("monte-carlo-gp_b200/csrc/native_kernel.cu", "monte-carlo-gp_b200/csrc/native_math.cuh",
+                  "monte-carlo-gp_b200/csrc/device_params.h")
 N_DRIVERS, LAPS = 20, 57
-WORKLOAD = "bahrain57: 20 drivers x 57 laps, native Philox4x32-10/FP32, synthetic inputs of SURVEY 8(d)"
+WORKLOAD = "bahrain57: 20 drivers x 57 laps, native Philox4x32-7/FP32, synthetic inputs of SURVEY 8(d)"
+HASH_SIMS, HASH_SEED = 8_000_000, 42   # the fixed global sim range whose count table is hashed (any N must agree)
+
+
+def load_json(rel):
+    try:
+        with open(os.path.join(ROOT, rel)) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
+def kernel_source_sha256() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for rel in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 def w_race(laps: int) -> int:
@@ -143,9 +162,10 @@ def reference_arm(args):
         "impl": "reference", "metric": "race-sims/sec (20 drv x 57 laps)", "value": value, "unit": "races/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD.replace("native Philox4x32-10/FP32", "reference MT19937/FP64 on CPU")},
+        "config": {"workload": WORKLOAD.replace("native Philox4x32-7/FP32", "reference MT19937/FP64 on CPU")},
         "driver_laps_per_s": value * N_DRIVERS * LAPS,
-        "cpu_baseline": {"value": value, "unit": "races/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "races/s", "cores": cores, "kind": "port", "sample": sample,
+                         "python_reference": load_json(PYTHON_REFERENCE)},
         "e2e": {"value": value, "unit": "races/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -235,12 +255,16 @@ def main():
     value = S * n_gpus * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: the public drop-in API with host buffers, copies inside the timed region --------------
+    # (every step passes a different `stream` id: the library skips derivation + upload for a batch identical to the
+    # resident one, and an end-to-end step has to pay for its inputs)
     e2e_steps = max(2, min(args.steps, 5))
     sim.run_monte_carlo_counts(S, *mc_args, seed=seed, sim_begin=rank * S)
     barrier()
+    h2d_params = 0
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        h = sim.run_monte_carlo_counts(S, *mc_args, seed=seed, sim_begin=((100 + k) * n_gpus + rank) * S)
+        h = sim.run_monte_carlo_counts(S, *mc_args, seed=seed, sim_begin=((100 + k) * n_gpus + rank) * S, stream=1 + k)
+        h2d_params = mcgp.capi.get_engine(local).last_upload_bytes()
         if world > 1:
             ht = torch.from_numpy(h.astype("int64")).to(dev)
             dist.all_reduce(ht)
@@ -252,8 +276,39 @@ def main():
     e2e_value = S * n_gpus * e2e_steps / float(e2e_t.item())
     # bytes per step: the += count table both ways, plus what the library uploads on every host-buffer call (the
     # derived parameter blocks and the overtake pace table, counted by the library itself)
-    h2d = N_DRIVERS * N_DRIVERS * 8 + mcgp.capi.get_engine(local).last_upload_bytes()
+    h2d = N_DRIVERS * N_DRIVERS * 8 + h2d_params
     d2h = N_DRIVERS * N_DRIVERS * 8
+
+    # ---- bit-identity across GPU counts: SHA-256 of the count table of a FIXED global sim range -----
+    # sims [0, HASH_SIMS) with seed HASH_SEED, sharded over the N ranks, one all-reduce: BENCH / SCALE lines of any N
+    # must carry the same hash (draws are keyed by the global sim index).
+    import hashlib
+    hh = sharded.run(HASH_SIMS, HASH_SEED)
+    torch.cuda.synchronize()
+    hist_sha256 = hashlib.sha256(hh.cpu().numpy().astype("<i8").tobytes()).hexdigest()
+
+    # ---- the product-sized call: run_monte_carlo(10 000) as src/predictor.py:283-291 makes it ----------
+    product = None
+    if rank == 0:
+        import statistics
+        lat = {}
+        for label, vary in (("fresh_params", True), ("resident_params", False)):
+            ts = []
+            for i in range(60):
+                t1 = time.perf_counter()
+                sim.run_monte_carlo_counts(10_000, *mc_args, seed=1000 + i, stream=(500 + i) if vary else 0)
+                ts.append(time.perf_counter() - t1)
+            lat[label] = 1e3 * statistics.median(ts[10:])
+        ts = []
+        for i in range(60):
+            t1 = time.perf_counter()
+            sim.run_monte_carlo(10_000, *mc_args, seed=2000 + i)
+            ts.append(time.perf_counter() - t1)
+        lat["run_monte_carlo_dicts_in_dict_out"] = 1e3 * statistics.median(ts[10:])
+        product = {"ms": lat["run_monte_carlo_dicts_in_dict_out"], "sims": 10_000, "calls": 50, "statistic": "median",
+                   "counts_api_fresh_params_ms": lat["fresh_params"], "counts_api_resident_params_ms": lat["resident_params"],
+                   "what": "RaceSimulator.run_monte_carlo(10 000, host dicts) -> {driver: {pos: p}} as src/predictor.py:283-291 calls it; "
+                           "fresh = parameters differ from the previous call (derived + uploaded), resident = same race again"}
 
     # ---- replay mode (BASELINE config 2), reported beside the headline ----------------------------
     # Throughput only (bit-exactness is tests/ and tests/replay_config2.py): synthetic uniform / normal tapes made
@@ -351,9 +406,14 @@ def main():
         cores = os.cpu_count() or 1
         n_cpu = args.cpu_sims or 120000 * cores   # ~12 s of CPU work
         dt, n_done = cpu_run(n_cpu, 42, cores)
+        pyref = load_json(PYTHON_REFERENCE)   # the unmodified Python reference, measured where /root/reference exists
         cpu = {"value": n_done / dt, "unit": "races/s", "cores": cores, "kind": "port",
                "sample": f"{n_done} sims of the same race, {cores} threads, {dt:.1f} s; C restatement of src/simulation.py "
-                         f"(bit-exact to the Python reference, which runs ~127 races/s/core)"}
+                         f"(bit-exact to the Python reference)",
+               "python_reference": None if pyref is None else {
+                   "races_per_s_per_core": pyref["races_per_s_per_core"], "races_per_s_total": pyref["races_per_s_total"],
+                   "cores": pyref["cores"], "measured_on": "build box (not this GPU box): " + pyref["where"],
+                   "how": pyref["what"] + f", {pyref['sims_per_worker']} sims per worker (tools/measure_python_reference.py)"}}
 
     if world > 1:
         dist.barrier()
@@ -365,6 +425,10 @@ def main():
         achieved = per_gpu * w_race(LAPS) / 1e12                 # Twarp-instr/s per GPU (algorithmic)
         peak = sm_count * 4 * f_max * 1e6 / 1e12
         peak_run = sm_count * 4 * f_run * 1e6 / 1e12
+        ncu = load_json(NCU_SUMMARY) or {}
+        executed = ncu.get("executed_warp_instr_per_unit")
+        traffic = None if ncu.get("dram_bytes_read") is None else ncu["dram_bytes_read"] + (ncu.get("dram_bytes_written") or 0)
+        build_sha = kernel_source_sha256()
         line = {
             "metric": "race-sims/sec (20 drv x 57 laps)", "value": value, "unit": "races/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -380,14 +444,22 @@ def main():
             "roofline": {"bound": "alu_issue", "achieved": achieved, "peak": peak, "unit": "Twarp-instr/s per GPU",
                          "frac": achieved / peak, "frac_at_sampled_clock": achieved / peak_run,
                          "algorithmic_warp_instr_per_race": w_race(LAPS), "sm_count": sm_count, "f_sm_mhz_max": f_max,
-                         "f_sm_mhz_sampled": f_run, "traffic": NCU["dram_bytes_per_launch"],
-                         "executed_warp_instr_per_race": NCU["executed_warp_instr_per_race"],
-                         "issue_slot_utilisation": per_gpu * NCU["executed_warp_instr_per_race"] / 1e12 / peak,
+                         "f_sm_mhz_sampled": f_run, "traffic": traffic,
+                         "executed_warp_instr_per_race": executed,
+                         "issue_slot_utilisation": None if executed is None else per_gpu * executed / 1e12 / peak,
+                         "ncu_issue_active_pct": ncu.get("issue_active_pct"),
+                         "capture": {"summary": NCU_SUMMARY if ncu else None, "kernel": ncu.get("kernel"),
+                                     "source_sha256": ncu.get("source_sha256"), "build_source_sha256": build_sha},
+                         "capture_matches_build": bool(ncu) and ncu.get("source_sha256") == build_sha,
                          "note": "no dense contraction and ~0 HBM traffic (SURVEY 8(d)): the bound is warp-instruction issue, "
                                  "N_SM x 4 x f_SM.  frac = ALGORITHMIC work (17 100 warp-instr per race, SURVEY 8(d)) / peak; "
-                                 "issue_slot_utilisation = instructions this kernel actually executes (ncu, "
-                                 + NCU["capture"] + ") x races/s / peak; traffic = dram bytes read+written during that launch (ncu): write-back of the preceding 256 MiB L2-flush fill, the kernel's own input is 27 KB per block"},
+                                 "issue_slot_utilisation = instructions this kernel actually executes per race (ncu capture "
+                                 "named in `capture`, same sources iff capture_matches_build) x races/s / peak; traffic = dram "
+                                 "bytes read + written by the captured launch (2 M races, no L2 fill before it)"},
             "cpu_baseline": cpu,
+            "hist_sha256": {"value": hist_sha256, "sims": HASH_SIMS, "seed": HASH_SEED,
+                            "what": "SHA-256 of the int64 count table of global sims [0, sims), sharded over the N ranks + all-reduce"},
+            "e2e_product_call_ms": product["ms"] if product else None, "product_call": product,
             "replay_mode": replay,
             "season_batch": aux.get("season_batch"), "trace_mode": aux.get("trace_mode"),
             "lap_histogram_mode": aux.get("lap_histogram_mode"),

@@ -20,7 +20,7 @@ cudaError_t launch_native(const NativeRace* races_dev, const PacePair* pace_dev,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
                           unsigned long long trace_first, unsigned long long trace_count, unsigned long long* laphist,
                           unsigned long long* work_counter, int sm_count, cudaStream_t st);
-cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
+cudaError_t launch_replay(const ReplayRace* race_dev, int n_drivers, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
                           unsigned long long* work_counter, int sm_count, cudaStream_t st);
@@ -658,7 +658,7 @@ int mcgp_launch_replay(mcgp_handle h, uint64_t n_sims, const double* u_py_dev, c
     if (rc) return rc;
     const cudaStream_t st = (cudaStream_t)cuda_stream;
     CU(order_before(h, st));
-    CU(mcgp::launch_replay(h->replay_dev, n_sims, u_py_dev, z_dev, u_np_dev, (const long long*)off_dev,
+    CU(mcgp::launch_replay(h->replay_dev, h->n_drivers, n_sims, u_py_dev, z_dev, u_np_dev, (const long long*)off_dev,
                            (unsigned long long*)hist_dev, finish_dev, times_dev, dnf_lap_dev, grid_dev,
                            (long long*)used_dev, status_dev, h->work_counter, h->sm_count, st));
     CU(order_after(h, st));

@@ -40,17 +40,21 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 // Keys go through 32 doubles of warp scratch: every lane reads them back with broadcast LDS.128s and counts the
 // strictly smaller ones (2 instructions per key instead of a 2-shuffle round trip per key); exact ties -- possible
 // here: VSC scaling, the 0.1 s floor of the overtake re-write -- show up as a hole in the rank set and are fixed up.
-__device__ __forceinline__ int rank_set(double v, uint32_t in_set, int lane, int n, double* S_key) {
+// NP = key pairs read (10 for fields of <= 20 cars, else 16: lanes outside the set hold +inf), fully unrolled.
+template <int NP>
+__device__ __forceinline__ int rank_set(double v, uint32_t in_set, int lane, double* S_key) {
     const bool member = (in_set >> lane) & 1u;
     S_key[lane] = member ? v : __longlong_as_double(0x7ff0000000000000ll);
     __syncwarp();
-    int cnt = 0;
+    int c0 = 0, c1 = 0;
     const double2* k2 = reinterpret_cast<const double2*>(S_key);
-    for (int j = 0; 2 * j < n; j++) {
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
         const double2 k = k2[j];
-        cnt += (k.x < v) ? 1 : 0;
-        cnt += (k.y < v) ? 1 : 0;
+        c0 += (k.x < v) ? 1 : 0;
+        c1 += (k.y < v) ? 1 : 0;
     }
+    int cnt = c0 + c1;
     const int m = __popc(in_set);
     const uint32_t want = m >= 32 ? RFULL : ((1u << m) - 1u);
     const uint32_t seen = __reduce_or_sync(RFULL, member ? (1u << (cnt & 31)) : 0u);
@@ -100,17 +104,43 @@ __device__ double py_sum(const double* P, const uint8_t* K, int n, int& result_k
     return r;
 }
 
+// The same sum() when every item is an exact float or an int 0 (`items`: lanes whose item is a float; warp-uniform):
+// int zeros add 0.0 to a non-negative partial sum (a no-op), so only the float items are visited, in index order, and
+// with non-negative terms Neumaier's branch `abs(r) >= abs(x)` is max / min.  Bit-identical to py_sum on such lists.
+__device__ __forceinline__ double py_sum_floats(const double* P, uint32_t items, int& result_kind) {
+    if (items == 0u) { result_kind = 0; return 0.0; }
+    double r = 0.0 + P[__ffs(items) - 1], c = 0.0;
+    for (uint32_t m = items & (items - 1u); m; m &= m - 1u) {
+        const double x = P[__ffs(m) - 1];
+        const double t = r + x;
+        c += (fmax(r, x) - t) + fmin(r, x);
+        r = t;
+    }
+    if (c != 0.0 && isfinite(c)) r += c;
+    result_kind = 1;
+    return r;
+}
+
+template <int NP>
 __global__ void __launch_bounds__(kRThreads)
 replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sims, const double* __restrict__ u_py,
                    const double* __restrict__ zt, const double* __restrict__ u_np, const long long* __restrict__ off,
                    unsigned long long* __restrict__ hist, uint8_t* __restrict__ finish, double* __restrict__ times,
                    int16_t* __restrict__ dnf_lap_out, uint8_t* __restrict__ grid_out, long long* __restrict__ used_out,
                    int* __restrict__ status, unsigned long long* __restrict__ work_counter) {
+    // draws one lap can consume at most: 4 event draws + n retirement tests + 3 passes x (n - 1) pairs (U_py), n normals (Z)
+    constexpr int kPyWin = NP == 10 ? 96 : 160, kZWin = 32;
     __shared__ ReplayRace R;
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     __shared__ __align__(16) double S_p_all[kRWarps][32];  // grid sampling items, then the rank keys
-    __shared__ uint8_t S_k_all[kRWarps][32];
+    __shared__ __align__(16) double S_c_all[kRWarps][32];  // running cumsum of the grid probabilities
     __shared__ uint32_t S_inv_all[kRWarps][32];
+    // Per-warp windows of the two lap-loop tapes, refilled once per lap with coalesced loads.  The draw sites of a lap
+    // (events, retirement tests, noise, <= 3 overtake passes) depend on each other's outcome, so reading the tapes
+    // from global memory where they are consumed cost 5-6 dependent DRAM/L2 round trips per lap (ncu r2b: 2.3 stall
+    // cycles per issue on the long scoreboard, 14 % of all samples on the tape load); now it is one.
+    __shared__ __align__(16) double S_py_all[kRWarps][kPyWin];
+    __shared__ __align__(16) double S_z_all[kRWarps][kZWin];
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(race);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&R);
@@ -120,8 +150,10 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* S_p = S_p_all[warp];
-    uint8_t* S_k = S_k_all[warp];
+    double* S_c = S_c_all[warp];
     uint32_t* S_inv = S_inv_all[warp];
+    double* S_py = S_py_all[warp];
+    double* S_z = S_z_all[warp];
     const int n = R.n, L = R.total_laps, track = R.track;
     const bool is_car = lane < n;
     const uint32_t nmask = n >= 32 ? RFULL : ((1u << n) - 1u);
@@ -141,16 +173,28 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         // ---- _sample_grid (src/simulation.py:102-145) + RandomState.choice restated -------------
         int drv = 0;
         {
+            // the n uniforms behind the n np.random.choice calls (:137): one coalesced read
+            const double u_mine = np.at(lane, is_car, err);
+            np.i += n;
             uint32_t remaining = nmask;  // by driver index
             for (int pos = 0; pos < n; pos++) {
                 // lane d prepares driver d's item :119-122
                 uint8_t kd = 0;
                 double pd = 0.0;
                 if (is_car && ((remaining >> lane) & 1u) && R.kind[lane][pos] != 0) { pd = R.grid[lane][pos]; kd = R.kind[lane][pos]; }
-                S_p[lane] = pd; S_k[lane] = kd;
+                S_p[lane] = pd;
+                const uint32_t m_float = __ballot_sync(RFULL, kd == 1), m_np = __ballot_sync(RFULL, kd == 2);
                 __syncwarp();
                 int tk;
-                const double total = py_sum(S_p, S_k, n, tk);  // :123
+                double total;  // :123
+                if (m_np == 0u) {
+                    total = py_sum_floats(S_p, m_float, tk);
+                } else {  // np.float64 items: CPython's sum() leaves its compensated loop (Q12) -- the general state machine
+                    uint8_t* S_k = reinterpret_cast<uint8_t*>(S_c);
+                    S_k[lane] = kd;
+                    __syncwarp();
+                    total = py_sum(S_p, S_k, n, tk);
+                }
                 __syncwarp();
                 if (total > 0) {  // :125-126
                     pd = pd / total;
@@ -166,6 +210,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) approx += shfl_d(approx, lane ^ d);
                 if (!__all_sync(RFULL, fabs(approx - 1.0) < 1e-9 - 1e-12)) {
+                    uint8_t* S_k = reinterpret_cast<uint8_t*>(S_c);
                     S_p[lane] = pd; S_k[lane] = kd;
                     __syncwarp();
                     const double prob_sum = py_sum(S_p, S_k, n, tk);  // :133
@@ -174,12 +219,16 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 }
                 S_p[lane] = pd;
                 __syncwarp();
-                // p.cumsum(); cdf /= cdf[-1]; searchsorted(u, side='right')
-                double acc = S_p[0], mine = acc;
-                for (int d = 1; d < n; d++) { acc = acc + S_p[d]; if (d == lane) mine = acc; }
+                // p.cumsum(); cdf /= cdf[-1]; searchsorted(u, side='right').  cumsum is a serial left-to-right loop:
+                // every lane runs it, the running sums go through shared memory and each lane picks up its own.
+                double acc = S_p[0];
+                S_c[0] = acc;
+#pragma unroll 4
+                for (int d = 1; d < n; d++) { acc = acc + S_p[d]; S_c[d] = acc; }
                 __syncwarp();
-                const double cdf = mine / acc;
-                const double u = np.at(0, true, err); np.i++;
+                const double cdf = (is_car ? S_c[lane] : acc) / acc;
+                __syncwarp();
+                const double u = shfl_d(u_mine, pos);
                 int sel = __popc(__ballot_sync(RFULL, is_car && cdf <= u));
                 if (sel > n - 1) sel = n - 1;
                 if (lane == pos) drv = sel;
@@ -200,6 +249,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         uint32_t used = 1u << comp;
         bool dnf = !is_car, drs = false;
         int dnf_lap = 0, pos_live = 0;
+        int lead = 0;  // lane of the leading runner as of the last update_positions (warp-uniform)
         double cum = 0.0, last = 0.0, tbl = 0.0, ahead_last = 0.0;
 
         // _calculate_lap_time :313-332, strictly left to right
@@ -213,22 +263,28 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             const double noise = 0.0 + sigma * z;
             return pace + tire_effect - fuel_effect + R.cdelta[comp] - drs_gain + noise;
         };
-        // _update_positions :538-560
-        auto update_positions = [&](int lap, bool drs_disabled) {
-            const uint32_t live_m = __ballot_sync(RFULL, !dnf);
-            const int r = rank_set(cum, live_m, lane, n, S_p);
-            if (!dnf) S_inv[r] = lane;
-            __syncwarp();
-            if (live_m) {
-                const int lead = (int)S_inv[0];
-                const int pl = (!dnf && r > 0) ? (int)S_inv[r - 1] : lane;
+        // _update_positions :538-560.  r_all: this car's rank among ALL cars by (time, grid slot) with S_inv the matching
+        // rank -> lane map -- the order the last overtake pass worked on when it changed nothing (have_r), else derived
+        // here.  The live order is its restriction to the runners (same tie-break), so no second sort is needed.
+        auto update_positions = [&](int lap, bool drs_disabled, bool have_r, int r_all) {
+            if (!have_r) {
+                r_all = rank_set<NP>(cum, nmask, lane, S_p);
+                __syncwarp();
+                if (is_car) S_inv[r_all] = lane;
+                __syncwarp();
+            }
+            const uint32_t LM = __reduce_or_sync(RFULL, (is_car && !dnf) ? (1u << r_all) : 0u);  // ranks held by runners
+            if (LM) {
+                lead = (int)S_inv[__ffs(LM) - 1];
+                const uint32_t below = (is_car && !dnf) ? (LM & ((1u << r_all) - 1u)) : 0u;
+                const int pl = below ? (int)S_inv[31 - __clz(below)] : lane;
                 const double t0 = shfl_d(cum, lead), tp = shfl_d(cum, pl), lp = shfl_d(last, pl);
                 if (!dnf) {
-                    pos_live = r;
+                    pos_live = __popc(below);
                     tbl = cum - t0;
-                    if (lap <= 2 || drs_disabled || r == 0) drs = false;
+                    if (lap <= 2 || drs_disabled || pos_live == 0) drs = false;
                     else drs = (cum - tp) < 1.0;
-                    ahead_last = r > 0 ? lp : 0.0;
+                    ahead_last = pos_live > 0 ? lp : 0.0;
                 }
             }
             __syncwarp();
@@ -253,21 +309,40 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 cum += lt;
                 age += 1;
             }
-            update_positions(1, true);
+            update_positions(1, true, false, 0);
         }
 
         int drs_until = 0;
         for (int lap = 2; lap <= L; lap++) {
+            // ---- this lap's windows of the tapes: one coalesced refill, then shared-memory reads ----
+            // pc / zc: draws of the window consumed so far.  A read past the end of the tape sets err (MCGP_ETAPE).
+#pragma unroll
+            for (int w = 0; w < kPyWin / 32; w++) {
+                const long long q = py.i + 32 * w + lane;
+                S_py[32 * w + lane] = q < py.e ? py.p[q] : 0.5;
+            }
+            {
+                const long long q = zz.i + lane;
+                S_z[lane] = q < zz.e ? zz.p[q] : 0.5;
+            }
+            __syncwarp();
+            int pc = 0, zc = 0;
+            auto py_draw = [&](int k, bool active) -> double {  // the k-th unread U_py draw (for the lanes that take one)
+                if (!active) return 0.5;
+                if (py.i + pc + k >= py.e) err = 1;
+                return S_py[pc + k];
+            };
+
             // ---- events :168-176 (short-circuit draws) ------------------------------------------
             int ev = 0;
             {
-                const double r1 = py.at(0, true, err); py.i++;
+                const double r1 = py_draw(0, true); pc++;
                 if (r1 < R.red_p) ev = 1;
                 else {
-                    const double r2 = py.at(0, true, err); py.i++;
+                    const double r2 = py_draw(0, true); pc++;
                     if (r2 < R.sc_p) ev = 2;
                     else {
-                        const double r3 = py.at(0, true, err); py.i++;
+                        const double r3 = py_draw(0, true); pc++;
                         if (r3 < R.vsc_p) ev = 3;
                     }
                 }
@@ -275,8 +350,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             if (ev) {
                 const uint32_t live_m = __ballot_sync(RFULL, !dnf);
                 if (live_m) {
-                    const int lead = (int)S_inv[0];  // still the live order of the last update_positions
-                    const double t0 = shfl_d(cum, lead);
+                    const double t0 = shfl_d(cum, lead);  // still the leader of the last update_positions
                     const int rem = L - lap;
                     if (ev == 1) {  // _handle_red_flag :397-431
                         if (!dnf) {
@@ -298,11 +372,11 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                             cum = t0 + gap * 0.8;
                             tbl = cum - t0;
                         }
-                        const double r4 = py.at(0, true, err); py.i++;  // drawn only when somebody is still running :381-392
+                        const double r4 = py_draw(0, true); pc++;  // drawn only when somebody is still running :381-392
                         if (r4 < 0.3 && !dnf) age = age - 1 > 0 ? age - 1 : 0;
                     }
                     // :179 re-sorts after the handler; a VSC can create exact ties, so re-derive the car ahead
-                    const int r = rank_set(cum, live_m, lane, n, S_p);
+                    const int r = rank_set<NP>(cum, live_m, lane, S_p);
                     __syncwarp();
                     if (!dnf) S_inv[r] = lane;
                     __syncwarp();
@@ -317,13 +391,18 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             // ---- per-car lap :186-223 (grid order == lane order) -------------------------------
             {
                 const uint32_t live_m = __ballot_sync(RFULL, !dnf);
-                const double u = py.at(__popc(live_m & lt_mask), !dnf, err);
-                py.i += __popc(live_m);
+                const double u = py_draw(__popc(live_m & lt_mask), !dnf);
+                pc += __popc(live_m);
                 const bool was_live = !dnf;
                 if (was_live && u < dnf_rate) { dnf = true; dnf_lap = lap; }
                 const uint32_t surv = __ballot_sync(RFULL, !dnf);
-                const double z = zz.at(__popc(surv & lt_mask), !dnf, err);
-                zz.i += __popc(surv);
+                const int zk = __popc(surv & lt_mask);
+                double z = 0.5;
+                if (!dnf) {
+                    if (zz.i + zk >= zz.e) err = 1;
+                    z = S_z[zk];
+                }
+                zc = __popc(surv);
                 if (!dnf) {
                     const double clean = lap_time(lap, z);
                     double lt = clean;
@@ -358,10 +437,12 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             }
 
             // ---- _simulate_overtakes :496-536 --------------------------------------------------
+            bool have_r = false;  // r / S_inv below describe the current times (the last pass changed nothing)
+            int r = 0;
             {
                 const double op = R.pace[drv] + (double)age * deg;  // :514-515 (raw driver deg)
                 for (int pass = 0; pass < 3; pass++) {
-                    const int r = rank_set(cum, nmask, lane, n, S_p);  // ALL cars, retired ones included (Q5)
+                    r = rank_set<NP>(cum, nmask, lane, S_p);  // ALL cars, retired ones included (Q5)
                     __syncwarp();
                     if (is_car) S_inv[r] = lane;
                     __syncwarp();
@@ -372,13 +453,13 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     if (drs) delta += R.drs_delta;
                     const bool cond = is_car && r > 0 && !dnf && !dnf_a && delta > R.ovt_delta;
                     const uint32_t CM = __reduce_or_sync(RFULL, cond ? (1u << r) : 0u);
-                    const double u = py.at(__popc(CM & ((1u << r) - 1u)), cond, err);  // draws in sorted order :524
-                    py.i += __popc(CM);
+                    const double u = py_draw(__popc(CM & ((1u << r) - 1u)), cond);  // draws in sorted order :524
+                    pc += __popc(CM);
                     double prob = delta / 2.0;
                     if (prob > 0.5) prob = 0.5;
                     const bool succ = cond && u < prob;
                     const uint32_t M = __reduce_or_sync(RFULL, succ ? (1u << r) : 0u);
-                    if (M == 0u) { __syncwarp(); break; }
+                    if (M == 0u) { have_r = true; __syncwarp(); break; }
                     // sequential re-write chain :528-530, replayed op by op for bit-exactness
                     const uint32_t clear_below = ~M & ((2u << r) - 1u);
                     const int j = 31 - __clz(clear_below);
@@ -394,7 +475,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     __syncwarp();
                 }
             }
-            update_positions(lap, lap <= drs_until);
+            py.i += pc;
+            zz.i += zc;
+            update_positions(lap, lap <= drs_until, have_r, r);
         }
 
         // ---- final classification :231-242 -------------------------------------------------------
@@ -402,12 +485,12 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             const uint32_t live_m = __ballot_sync(RFULL, !dnf);
             const int n_live = __popc(live_m & nmask);
             int worse = 0;
-            for (int j = 0; j < n; j++) {
+            // retired cars only: sorted(key=(lap, cumulative_time), reverse=True) is stable -- equal keys keep grid order
+            for (uint32_t dm = ~live_m & nmask; dm; dm &= dm - 1u) {
+                const int j = __ffs(dm) - 1;
                 const int jl = __shfl_sync(RFULL, dnf_lap, j);
                 const double jt = shfl_d(cum, j);
-                const bool jd = __shfl_sync(RFULL, (int)dnf, j) != 0;
-                // sorted(key=(lap, cumulative_time), reverse=True) is stable: equal keys keep grid order
-                const bool ahead = jd && j != lane && (jl > dnf_lap || (jl == dnf_lap && (jt > cum || (jt == cum && j < lane))));
+                const bool ahead = j != lane && (jl > dnf_lap || (jl == dnf_lap && (jt > cum || (jt == cum && j < lane))));
                 worse += ahead ? 1 : 0;
             }
             if (is_car) {
@@ -436,17 +519,22 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     }
 }
 
-cudaError_t launch_replay(const ReplayRace* race_dev, unsigned long long n_sims, const double* u_py, const double* z,
+cudaError_t launch_replay(const ReplayRace* race_dev, int n_drivers, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
                           unsigned long long* work_counter, int sm_count, cudaStream_t st) {
-    long long blocks = (long long)sm_count * 5;  // 92 registers x 128 threads: five blocks are resident per SM
+    auto kern = n_drivers <= 20 ? replay_race_kernel<10> : replay_race_kernel<16>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    long long blocks = (long long)sm_count * per_sm;  // as many blocks as are resident at once; sims are claimed dynamically
     const long long need = (long long)((n_sims + kRWarps - 1) / kRWarps);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     init_work_counters<<<1, 32, 0, st>>>(work_counter, 1, (unsigned long long)blocks * kRWarps);
-    replay_race_kernel<<<(unsigned)blocks, kRThreads, 0, st>>>(race_dev, n_sims, u_py, z, u_np, off, hist, finish, times,
-                                                            dnf_lap, grid, used, status, work_counter);
+    kern<<<(unsigned)blocks, kRThreads, 0, st>>>(race_dev, n_sims, u_py, z, u_np, off, hist, finish, times,
+                                                 dnf_lap, grid, used, status, work_counter);
     return cudaGetLastError();
 }
 
