@@ -163,6 +163,42 @@ uint64_t mcgp_last_upload_bytes(mcgp_handle h);
  * out must hold rows * stride * 4 floats. */
 int mcgp_pace_table(const mcgp_race_params* race, int32_t* rows, int32_t* stride, float* out);
 
+/* scoring on the device (reference src/validation.py:82-158) ------------------------------------- *
+ * Win / podium / points tallies, the per-race Brier term of the win probabilities, podium hits and the calibration
+ * bins computed from count tables that STAY on the GPU (hist_dev: device pointer, [n_races][n][n] as the native
+ * launches leave it); only the small results come back.  winner[r] = driver index of the actual winner of race r or
+ * -1 (race skipped, brier[r] = NaN: brier_score's `actual is None`); podium[r][3] = actual podium or -1 (skipped,
+ * podium_hits[r] = -1); podium may be NULL.
+ *   tallies     [n_races][3][n]  counts of P1 / top-3 / top-10 finishes per driver
+ *   brier       [n_races]        mean_d (count[d][P1] / n_sims - [d == winner])^2   (:82-106; the season score is their mean)
+ *   podium_hits [n_races]        |three highest podium probabilities  ∩  actual podium|  (:109-130)
+ *   calib       [3][10]          per bin of np.linspace(0, 1, bins + 1): pairs, sum of outcomes, sum of probabilities (:133-158)
+ *   calib_bins  [1]              bins = min(10, max(2, pairs / 10))
+ * All outputs are host pointers and may be NULL; the call synchronises `cuda_stream`. */
+int mcgp_score_counts(mcgp_handle h, const uint64_t* hist_dev, int n_races, int n_drivers, uint64_t n_sims,
+                      const int32_t* winner, const int32_t* podium, uint64_t* tallies, double* brier,
+                      int32_t* podium_hits, double* calib, int32_t* calib_bins, void* cuda_stream);
+
+/* A device-resident season: simulate race r -> update the pairwise Elo ratings with its result -> derive race r+1's
+ * grid probabilities from the new qualifying ratings -> next launch, all on one stream with no host round trip
+ * (reference: backtest_model's loop src/validation.py:176-198, F1EloSystem src/elo.py:45-141, _predict_quali /
+ * _adjust_for_penalties src/predictor.py:321-407).  grid_probs of `races` is ignored: race r's grid block is derived
+ * on the device from the qualifying ratings before it.  The "actual" result of race r is its sim number n_sims (the
+ * one after the counted range): its sampled grid is the qualifying result, its finishing order the race result.
+ *   quali0 / race0 [n]            ratings before the first race;  k_factor: F1EloSystem.k
+ *   penalties      [n_races][n]   grid places lost per driver (0 = none), may be NULL
+ *   hist           [n_races][n][n]  count tables (overwritten, not accumulated)
+ *   quali_hist / race_hist [n_races + 1][n]  ratings before each race and after the last
+ *   grid_rows      [n_races][n][n]  the derived grid_probs [driver][position] (FP64, before the float conversion)
+ *   actual_grid / actual_finish [n_races][n]  driver index per grid slot / finishing position of the actual sims
+ *   tallies, brier, podium_hits, calib, calib_bins: as mcgp_score_counts, scored against the actual results
+ * All outputs are host pointers and may be NULL. */
+int mcgp_run_season(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims, uint64_t seed,
+                    uint32_t flags, double k_factor, const double* quali0, const double* race0,
+                    const int32_t* penalties, uint64_t* hist, double* quali_hist, double* race_hist,
+                    double* grid_rows, uint8_t* actual_grid, uint8_t* actual_finish, uint64_t* tallies,
+                    double* brier, int32_t* podium_hits, double* calib, int32_t* calib_bins);
+
 /* replay mode: FP64, consumes the reference's own draws, bit-exact ------------------------------ *
  * Sim s reads u_py[off[3s]..off[3s+3]) (random.random() values, :168-194,:287,:392,:524),
  * z[off[3s+1]..) (standard normals; np.random.normal(0,s) = 0 + s*z, :302,:330) and

@@ -4,4 +4,4 @@ The directory name carries a hyphen (it mirrors the upstream repository name), s
 ``importlib.import_module("monte-carlo-gp_b200")`` or through the top-level alias ``mcgp_b200``.
 Submodules are imported lazily; nothing here needs a GPU until a simulation is launched.
 """
-__all__ = ["simulation", "workloads", "capi", "distributed", "scoring", "grid_model", "ratings", "params_io"]
+__all__ = ["simulation", "workloads", "capi", "distributed", "scoring", "grid_model", "ratings", "params_io", "season"]

@@ -78,6 +78,9 @@ _SIGNATURES = {
                                              C.c_void_p, C.c_void_p]),
     "mcgp_run_native_laphist": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int, C.c_uint64, C.c_uint64,
                                           C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "mcgp_score_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64] + [C.c_void_p] * 8),
+    "mcgp_run_season": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_int, C.c_uint64, C.c_uint64, C.c_uint32,
+                                  C.c_double] + [C.c_void_p] * 14),
     "mcgp_run_replay": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_uint64] + [C.c_void_p] * 10),
     "mcgp_launch_replay": (C.c_int, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 12),
 }
@@ -219,6 +222,36 @@ class Engine:
         """Asynchronous launch on device-resident buffers (raw device pointers)."""
         self._check(self._lib.mcgp_launch_native(self._h, n_sims, sim_begin, seed & (2 ** 64 - 1), flags, _p(hist_ptr),
                                                  _p(finish_ptr), _p(times_ptr), _p(stream)))
+
+    # ---- scoring / device-resident season ------------------------------------------------------
+    def score_counts(self, hist_ptr, n_races: int, n: int, n_sims: int, winners, podiums=None, stream=None) -> dict:
+        """Scores count tables that live on the GPU (include/mcgp.h: mcgp_score_counts); only the results come back."""
+        winners = np.ascontiguousarray(winners, np.int32)
+        podiums = None if podiums is None else np.ascontiguousarray(podiums, np.int32).reshape(n_races, 3)
+        out = dict(tallies=np.zeros((n_races, 3, n), np.uint64), brier=np.zeros(n_races, np.float64),
+                   podium_hits=np.zeros(n_races, np.int32), calib=np.zeros((3, 10), np.float64), calib_bins=np.zeros(1, np.int32))
+        self._check(self._lib.mcgp_score_counts(self._h, _p(hist_ptr), n_races, n, n_sims, _p(winners), _p(podiums), _p(out["tallies"]),
+                                                _p(out["brier"]), _p(out["podium_hits"]), _p(out["calib"]), _p(out["calib_bins"]),
+                                                _p(stream)))
+        return out
+
+    def run_season(self, races, n_sims: int, seed: int, quali0, race0, k_factor: float = 32.0, penalties=None,
+                   flags: int = 0) -> dict:
+        """The device-resident season loop (include/mcgp.h: mcgp_run_season)."""
+        arr, R, n = self._pack(races)
+        q0, r0 = np.ascontiguousarray(quali0, np.float64), np.ascontiguousarray(race0, np.float64)
+        assert q0.shape == (n,) and r0.shape == (n,)
+        pen = None if penalties is None else np.ascontiguousarray(penalties, np.int32).reshape(R, n)
+        out = dict(hist=np.zeros((R, n, n), np.uint64), quali=np.zeros((R + 1, n)), race=np.zeros((R + 1, n)),
+                   grid_rows=np.zeros((R, n, n)), actual_grid=np.zeros((R, n), np.uint8), actual_finish=np.zeros((R, n), np.uint8),
+                   tallies=np.zeros((R, 3, n), np.uint64), brier=np.zeros(R), podium_hits=np.zeros(R, np.int32),
+                   calib=np.zeros((3, 10)), calib_bins=np.zeros(1, np.int32))
+        self._check(self._lib.mcgp_run_season(
+            self._h, arr, R, n_sims, seed & (2 ** 64 - 1), flags, float(k_factor), _p(q0), _p(r0), _p(pen), _p(out["hist"]),
+            _p(out["quali"]), _p(out["race"]), _p(out["grid_rows"]), _p(out["actual_grid"]), _p(out["actual_finish"]),
+            _p(out["tallies"]), _p(out["brier"]), _p(out["podium_hits"]), _p(out["calib"]), _p(out["calib_bins"])))
+        self.n_races = self.n_drivers = 0
+        return out
 
     # ---- replay mode ---------------------------------------------------------------------------
     def run_replay(self, race: McgpRaceParams, u_py, z, u_np, off, detail: bool = True) -> dict:

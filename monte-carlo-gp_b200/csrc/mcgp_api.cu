@@ -19,11 +19,19 @@ cudaError_t launch_native(const NativeRace* races_dev, const PacePair* pace_dev,
                           unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
                           unsigned long long trace_first, unsigned long long trace_count, unsigned long long* laphist,
-                          unsigned long long* work_counter, int sm_count, cudaStream_t st);
+                          unsigned long long* work_counter, int sm_count, cudaStream_t st, uint8_t* grid_out = nullptr);
 cudaError_t launch_replay(const ReplayRace* race_dev, int n_drivers, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
                           unsigned long long* work_counter, int sm_count, cudaStream_t st);
+cudaError_t launch_season_grid(NativeRace* race_dev, const double* quali_dev, const int32_t* penalty_dev, const double* teammate_dev,
+                               const double* form_dev, const double* circuit_dev, int n, double* rows_dev, cudaStream_t st);
+cudaError_t launch_season_elo(const uint8_t* grid_order, const uint8_t* finish_order, const double* q_before, const double* r_before,
+                              double* q_after, double* r_after, int n, double k, cudaStream_t st);
+cudaError_t launch_season_actual(const uint8_t* finish_order, int32_t* winner, int32_t* podium, int n, cudaStream_t st);
+cudaError_t launch_score_counts(const unsigned long long* hist, int n_races, int n, unsigned long long n_sims, const int32_t* winner,
+                                const int32_t* podium, unsigned long long* tallies, double* brier, int32_t* podium_hits,
+                                double* calib, int32_t* calib_bins, cudaStream_t st);
 int native_philox_rounds();
 size_t pace_pairs_per_race(int rows, int stride);  // device form of one race's overtake pace tables (device_params.h: PacePair)
 }  // namespace mcgp
@@ -640,6 +648,116 @@ int mcgp_run_native(mcgp_handle h, const mcgp_race_params* races, int n_races, u
     if (times_host && tim_bytes) CU(cudaMemcpyAsync(times_host, tim_dev, tim_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(hist_host, hist_pin, hist_bytes);
+    return MCGP_OK;
+}
+
+// ---- scoring and the device-resident season (kernels in season_kernels.cu) -------------------
+int mcgp_score_counts(mcgp_handle h, const uint64_t* hist_dev, int n_races, int n_drivers, uint64_t n_sims, const int32_t* winner,
+                      const int32_t* podium, uint64_t* tallies, double* brier, int32_t* podium_hits, double* calib,
+                      int32_t* calib_bins, void* cuda_stream) {
+    if (!h) return MCGP_EINVAL;
+    if (!hist_dev || !winner || n_races < 1 || n_drivers < 1 || n_drivers > MCGP_MAX_DRIVERS || n_sims == 0)
+        return fail(h, MCGP_EINVAL, "mcgp_score_counts: bad argument");
+    DeviceGuard g(h->device);
+    if (g.status != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(g.status));
+    const size_t R = (size_t)n_races, n = (size_t)n_drivers;
+    // one scratch block: winner | podium | tallies | brier | hits | calib | bins
+    const size_t o_win = 0, o_pod = o_win + R * 4, o_tal = (o_pod + R * 12 + 7) & ~(size_t)7, o_bri = o_tal + R * 3 * n * 8,
+                 o_cal = o_bri + R * 8, o_hit = o_cal + 30 * 8, o_bin = o_hit + R * 4, total = o_bin + 8;
+    void* blk = nullptr;
+    int rc = scratch_get(h, 7, total, &blk);
+    if (rc) return rc;
+    char* b = (char*)blk;
+    const cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU(cudaMemcpyAsync(b + o_win, winner, R * 4, cudaMemcpyHostToDevice, st));
+    if (podium) CU(cudaMemcpyAsync(b + o_pod, podium, R * 12, cudaMemcpyHostToDevice, st));
+    CU(mcgp::launch_score_counts((const unsigned long long*)hist_dev, n_races, n_drivers, n_sims, (const int32_t*)(b + o_win),
+                                 podium ? (const int32_t*)(b + o_pod) : nullptr, (unsigned long long*)(b + o_tal), (double*)(b + o_bri),
+                                 (int32_t*)(b + o_hit), (double*)(b + o_cal), (int32_t*)(b + o_bin), st));
+    if (tallies) CU(cudaMemcpyAsync(tallies, b + o_tal, R * 3 * n * 8, cudaMemcpyDeviceToHost, st));
+    if (brier) CU(cudaMemcpyAsync(brier, b + o_bri, R * 8, cudaMemcpyDeviceToHost, st));
+    if (podium_hits) CU(cudaMemcpyAsync(podium_hits, b + o_hit, R * 4, cudaMemcpyDeviceToHost, st));
+    if (calib) CU(cudaMemcpyAsync(calib, b + o_cal, 30 * 8, cudaMemcpyDeviceToHost, st));
+    if (calib_bins) CU(cudaMemcpyAsync(calib_bins, b + o_bin, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    h->launches = 1;
+    return MCGP_OK;
+}
+
+int mcgp_run_season(mcgp_handle h, const mcgp_race_params* races, int n_races, uint64_t n_sims, uint64_t seed, uint32_t flags,
+                    double k_factor, const double* quali0, const double* race0, const int32_t* penalties, uint64_t* hist,
+                    double* quali_hist, double* race_hist, double* grid_rows, uint8_t* actual_grid, uint8_t* actual_finish,
+                    uint64_t* tallies, double* brier, int32_t* podium_hits, double* calib, int32_t* calib_bins) {
+    if (!h) return MCGP_EINVAL;
+    if (!races || n_races < 1 || !quali0 || !race0 || n_sims == 0) return fail(h, MCGP_EINVAL, "mcgp_run_season: bad argument");
+    if (n_sims >= 0xffffffffull) return fail(h, MCGP_EINVAL, "at most 2^32 - 2 sims per race");
+    DeviceGuard g(h->device);
+    if (g.status != cudaSuccess) return fail(h, MCGP_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(g.status));
+    const cudaStream_t st = h->own_stream;
+    int rc = upload_native(h, races, n_races, st, true);
+    if (rc) return rc;
+    drop_resident(h);   // the grid blocks are rewritten on the device below: the resident copy no longer mirrors `races`
+    h->n_races = n_races; h->n_drivers = races[0].n_drivers;
+    const size_t R = (size_t)n_races, n = (size_t)h->n_drivers, nn = n * n;
+    const size_t per_race_pairs = mcgp::pace_pairs_per_race(h->pace_rows, h->pace_stride);
+    // device scratch: hist | scratch hist of the "actual" sims | q_hist | r_hist | rows | tallies | brier | calib | penalties |
+    //                 winner | podium | hits | bins | a_grid | a_finish
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return at; };
+    const size_t o_hist = take(R * nn * 8), o_hscr = take(nn * 8), o_q = take((R + 1) * n * 8), o_r = take((R + 1) * n * 8),
+                 o_rows = take(R * nn * 8), o_tal = take(R * 3 * n * 8), o_bri = take(R * 8), o_cal = take(30 * 8),
+                 o_pen = take(R * n * 4), o_win = take(R * 4), o_pod = take(R * 12), o_hit = take(R * 4), o_bin = take(16),
+                 o_ag = take(R * n), o_af = take(R * n);
+    void* blk = nullptr;
+    if ((rc = scratch_get(h, 6, o, &blk))) return rc;
+    char* b = (char*)blk;
+    CU(cudaMemsetAsync(b + o_hist, 0, o_q - o_hist, st));   // the count tables and the scratch table of the actual sims
+    CU(cudaMemcpyAsync(b + o_q, quali0, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b + o_r, race0, n * 8, cudaMemcpyHostToDevice, st));
+    if (penalties) CU(cudaMemcpyAsync(b + o_pen, penalties, R * n * 4, cudaMemcpyHostToDevice, st));
+    int launches = 0;
+    for (int r = 0; r < n_races; r++) {
+        NativeRace* race_dev = h->native_dev + r;
+        const double* q_r = (const double*)(b + o_q) + (size_t)r * n;
+        const double* r_r = (const double*)(b + o_r) + (size_t)r * n;
+        uint8_t* ag = (uint8_t*)(b + o_ag) + (size_t)r * n;
+        uint8_t* af = (uint8_t*)(b + o_af) + (size_t)r * n;
+        // quali ratings -> this race's grid rows, written into its parameter block in place
+        CU(mcgp::launch_season_grid(race_dev, q_r, penalties ? (const int32_t*)(b + o_pen) + (size_t)r * n : nullptr, nullptr, nullptr,
+                                    nullptr, (int)n, (double*)(b + o_rows) + (size_t)r * nn, st));
+        // the race: n_sims sims into this race's count table ...
+        CU(mcgp::launch_native(race_dev, h->pace_dev + per_race_pairs * r, h->pace_rows, h->pace_stride, 1, (int)n, n_sims, 0, seed,
+                               (flags & MCGP_F_EXACT_NORMAL) != 0, (unsigned long long*)(b + o_hist) + (size_t)r * nn, nullptr, nullptr,
+                               nullptr, 0, 0, nullptr, h->work_counter + r, h->sm_count, st));
+        // ... and one more (global sim index n_sims) whose grid and finishing order stand in for what really happened
+        CU(mcgp::launch_native(race_dev, h->pace_dev + per_race_pairs * r, h->pace_rows, h->pace_stride, 1, (int)n, 1, n_sims, seed,
+                               (flags & MCGP_F_EXACT_NORMAL) != 0, (unsigned long long*)(b + o_hscr), af, nullptr, nullptr, 0, 0, nullptr,
+                               h->work_counter + r, h->sm_count, st, ag));
+        CU(mcgp::launch_season_actual(af, (int32_t*)(b + o_win) + r, (int32_t*)(b + o_pod) + 3 * r, (int)n, st));
+        // pairwise Elo: quali ratings from the actual grid, race ratings from the actual finishing order -> next race
+        CU(mcgp::launch_season_elo(ag, af, q_r, r_r, (double*)(b + o_q) + (size_t)(r + 1) * n, (double*)(b + o_r) + (size_t)(r + 1) * n,
+                                   (int)n, k_factor, st));
+        launches += 7;
+    }
+    CU(mcgp::launch_score_counts((const unsigned long long*)(b + o_hist), n_races, (int)n, n_sims, (const int32_t*)(b + o_win),
+                                 (const int32_t*)(b + o_pod), (unsigned long long*)(b + o_tal), (double*)(b + o_bri),
+                                 (int32_t*)(b + o_hit), (double*)(b + o_cal), (int32_t*)(b + o_bin), st));
+    CU(order_after(h, st));
+    if (hist) CU(cudaMemcpyAsync(hist, b + o_hist, R * nn * 8, cudaMemcpyDeviceToHost, st));
+    if (quali_hist) CU(cudaMemcpyAsync(quali_hist, b + o_q, (R + 1) * n * 8, cudaMemcpyDeviceToHost, st));
+    if (race_hist) CU(cudaMemcpyAsync(race_hist, b + o_r, (R + 1) * n * 8, cudaMemcpyDeviceToHost, st));
+    if (grid_rows) CU(cudaMemcpyAsync(grid_rows, b + o_rows, R * nn * 8, cudaMemcpyDeviceToHost, st));
+    if (actual_grid) CU(cudaMemcpyAsync(actual_grid, b + o_ag, R * n, cudaMemcpyDeviceToHost, st));
+    if (actual_finish) CU(cudaMemcpyAsync(actual_finish, b + o_af, R * n, cudaMemcpyDeviceToHost, st));
+    if (tallies) CU(cudaMemcpyAsync(tallies, b + o_tal, R * 3 * n * 8, cudaMemcpyDeviceToHost, st));
+    if (brier) CU(cudaMemcpyAsync(brier, b + o_bri, R * 8, cudaMemcpyDeviceToHost, st));
+    if (podium_hits) CU(cudaMemcpyAsync(podium_hits, b + o_hit, R * 4, cudaMemcpyDeviceToHost, st));
+    if (calib) CU(cudaMemcpyAsync(calib, b + o_cal, 30 * 8, cudaMemcpyDeviceToHost, st));
+    if (calib_bins) CU(cudaMemcpyAsync(calib_bins, b + o_bin, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    h->launches = launches + 1;
+    // nothing valid stays resident: the parameter blocks now hold device-derived grids
+    h->n_races = 0; h->n_drivers = 0;
     return MCGP_OK;
 }
 

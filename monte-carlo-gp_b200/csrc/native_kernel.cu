@@ -158,7 +158,7 @@ __device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int 
 #pragma unroll 1
         for (int j = 0; j < lane; j++) cnt += (S_t[j] == t) ? 1 : 0;
     }
-    WARP_FENCE();
+    // (no trailing fence: the only caller, full_rank, fences right after publishing the records, before S_t can be rewritten)
     return cnt;
 }
 
@@ -176,6 +176,7 @@ struct Tables {  // per-lane view of the compound tables in shared memory
 struct NativeOutputs {
     uint8_t* finish;            // [race][sim][pos]  driver index
     float* times;               // [race][sim][driver] final gap to the winner
+    uint8_t* grid;              // [race][sim][slot]  driver index on each grid slot (_sample_grid's result)
     TraceRecord* trace;         // [race][sim - trace_first][lap][driver]
     unsigned long long trace_first, trace_count;  // window of sims (indices within the launch) that are traced
     unsigned long long* laphist;  // [race][lap][driver][pos] running-position counts after every lap (kOut == 3)
@@ -202,6 +203,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     __shared__ __align__(16) float S_t_all[kWarps][32];
     __shared__ float S_w_all[kWarps][48];              // window scratch: times by OLD rank, -inf / +inf pads
+    __shared__ float S_l_all[kWarps][34];              // last lap times by rank (update_positions), [0] = -inf pad
     // Records by rank: {time, overtake pace (NaN = retired)}, 8 bytes.  A rank-indexed access is a random permutation over the
     // banks; as 16-byte records (round 1: + last lap, padding) each exchange cost 8-10 shared-memory wavefronts instead of
     // the 4 a contiguous access needs, and the LSU data pipe ran at 77 % of its peak -- as busy as the issue port (ncu r2a).
@@ -248,7 +250,10 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
     if (lane < 16) W[lane + 24] = kInf;
     if (lane < 2) REC[lane - 2] = make_float2(-kInf, kNaN);
     __syncwarp();
-    const uint32_t w_sh = smem_u32(W), rec_sh = smem_u32(REC);
+    float* LST = S_l_all[warp] + 1;  // LST[-1] = -inf: the leader has no car ahead
+    if (lane == 0) LST[-1] = -kInf;
+    __syncwarp();
+    const uint32_t w_sh = smem_u32(W), rec_sh = smem_u32(REC), lst_sh = smem_u32(LST);
     uint32_t grid_sh = smem_u32(&R.grid[0][lane]);
     asm volatile("" : "+r"(grid_sh));  // (kept in a register: recomputing a shared-window address costs 6 instructions)
     const int n = __shfl_sync(FULL, R.n, 0), L = __shfl_sync(FULL, R.total_laps, 0), track = __shfl_sync(FULL, R.track, 0);
@@ -413,8 +418,9 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
             const bool pd = prev.y != prev.y;
             const uint32_t B = __ballot_sync(FULL, live && pd);
             bool has_pred = live && !pd;
-            // last lap times by rank, through the window scratch (window_place rewrites every slot before it reads)
-            const uint32_t wl = w_sh + 4u * (uint32_t)rank;
+            // last lap times by rank through their own scratch array: the next write is a lap (and several fences) away,
+            // so only the store -> load direction needs ordering here
+            const uint32_t wl = lst_sh + 4u * (uint32_t)rank;
             sts_f<0>(wl, last);
             XCHG_FENCE();
             float tl, t_pred = prev.x, last_pred = lds_f<-4>(wl);  // (rank 0 reads the -inf pad: no car ahead)
@@ -427,12 +433,10 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 has_pred = below != 0u;
                 const int rp = has_pred ? 31 - __clz(below) : 0;
                 t_pred = lds_f<0>(rec_sh + 8u * (uint32_t)rp);
-                last_pred = lds_f<0>(w_sh + 4u * (uint32_t)rp);
+                last_pred = lds_f<0>(lst_sh + 4u * (uint32_t)rp);
             } else {  // nobody left running: times stay as they are
-                XCHG_FENCE();
                 return;
             }
-            XCHG_FENCE();  // (the scratch is rewritten by the next lap's window_place)
             const bool drs_now = has_pred && lap > drs_until && (__fadd_rn(t, -t_pred) < 1.0f);
             if (kTrace) tr_drs = drs_now;
             drsf = drs_now ? 1.0f : 0.0f;
@@ -575,7 +579,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
                 set_rank(rank + (int)moved);
-                XCHG_FENCE();  // (every lane has read its window before W / REC are rewritten)
+                // (no fence needed here: REC was last READ before the fence above, W is not written again in this call)
                 sts_f2<0>(ra, t, op32);
                 const uint32_t cover = __reduce_or_sync(FULL, bit);
                 XCHG_FENCE();
@@ -676,6 +680,7 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                     const unsigned long long o = ((unsigned long long)race * n_sims + s) * (unsigned long long)n;
                     if (finish) finish[o + pos] = (uint8_t)lane;
                     if (times) times[o + lane] = t;
+                    if (out.grid) out.grid[o + slot] = (uint8_t)lane;
                 }
             }
         }
@@ -754,16 +759,16 @@ cudaError_t launch_native(const NativeRace* races_dev, const PacePair* pace_dev,
                           int max_n, unsigned long long n_sims, unsigned long long sim_begin, unsigned long long seed, bool exact,
                           unsigned long long* hist, uint8_t* finish, float* times, TraceRecord* trace,
                           unsigned long long trace_first, unsigned long long trace_count, unsigned long long* laphist,
-                          unsigned long long* work_counter, int sm_count, cudaStream_t st) {
+                          unsigned long long* work_counter, int sm_count, cudaStream_t st, uint8_t* grid_out) {
     static_assert(2 * sizeof(PacePair) == sizeof(uint4), "pace table entries are staged two to a 16-byte word");
-    const int kout = laphist ? 3 : trace ? 2 : (finish != nullptr || times != nullptr) ? 1 : 0;
+    const int kout = laphist ? 3 : trace ? 2 : (finish != nullptr || times != nullptr || grid_out != nullptr) ? 1 : 0;
     LaunchArgs a;
     a.races = races_dev; a.ptab = reinterpret_cast<const uint4*>(pace_dev); a.pt_rows = pace_rows; a.pt_stride = pace_stride;
     a.n_sims = n_sims; a.sim_begin = sim_begin;
     a.key = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
     a.hist = hist;
     const int lh_cells = laphist ? (pace_rows - 5) * max_n * max_n : 0;  // laps of the longest race x n x n
-    a.out = NativeOutputs{finish, times, trace, trace_first, trace ? trace_count : 0ull, laphist, lh_cells};
+    a.out = NativeOutputs{finish, times, grid_out, trace, trace_first, trace ? trace_count : 0ull, laphist, lh_cells};
     a.wc = work_counter; a.n_races = n_races; a.sm_count = sm_count; a.st = st;
     a.dyn_smem = pace_pairs_per_race(pace_rows, pace_stride) * sizeof(PacePair)  // both tables + padding (lanes without a car)
                  + (size_t)lh_cells * sizeof(uint32_t);

@@ -49,10 +49,10 @@ __device__ __forceinline__ int rank_set(double v, uint32_t in_set, int lane, dou
     int c0 = 0, c1 = 0;
     const double2* k2 = reinterpret_cast<const double2*>(S_key);
 #pragma unroll
-    for (int j = 0; j < NP; j++) {
+    for (int j = 0; j < NP; j++) {  // DSETP + predicated add per key (the plain C form compiles to three instructions)
         const double2 k = k2[j];
-        c0 += (k.x < v) ? 1 : 0;
-        c1 += (k.y < v) ? 1 : 0;
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c0) : "d"(k.x), "d"(v));
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c1) : "d"(k.y), "d"(v));
     }
     int cnt = c0 + c1;
     const int m = __popc(in_set);
@@ -313,23 +313,38 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         }
 
         int drs_until = 0;
-        for (int lap = 2; lap <= L; lap++) {
-            // ---- this lap's windows of the tapes: one coalesced refill, then shared-memory reads ----
-            // pc / zc: draws of the window consumed so far.  A read past the end of the tape sets err (MCGP_ETAPE).
+        // The windows of lap l + 1 are fetched into registers at the END of lap l (the cursors are final once the
+        // overtake passes are through), so the loads fly under update_positions and only land in shared memory here.
+        double win_py[kPyWin / 32], win_z;
+        auto fetch_windows = [&]() {
 #pragma unroll
             for (int w = 0; w < kPyWin / 32; w++) {
                 const long long q = py.i + 32 * w + lane;
-                S_py[32 * w + lane] = q < py.e ? py.p[q] : 0.5;
+                win_py[w] = q < py.e ? py.p[q] : 0.5;
             }
-            {
-                const long long q = zz.i + lane;
-                S_z[lane] = q < zz.e ? zz.p[q] : 0.5;
-            }
+            const long long q = zz.i + lane;
+            win_z = q < zz.e ? zz.p[q] : 0.5;
+        };
+#ifndef MCGP_REPLAY_LATE_FETCH
+        fetch_windows();
+#endif
+        for (int lap = 2; lap <= L; lap++) {
+#ifdef MCGP_REPLAY_LATE_FETCH
+            fetch_windows();
+#endif
+            // ---- this lap's windows of the tapes: one coalesced refill, then shared-memory reads ----
+            // pc / zc: draws of the window consumed so far.  A read past the end of the tape sets err (MCGP_ETAPE).
+#pragma unroll
+            for (int w = 0; w < kPyWin / 32; w++) S_py[32 * w + lane] = win_py[w];
+            S_z[lane] = win_z;
             __syncwarp();
             int pc = 0, zc = 0;
+            const long long py_left64 = py.e - py.i, z_left64 = zz.e - zz.i;
+            const int py_left = py_left64 > kPyWin ? kPyWin : (int)py_left64;  // draws left on the tape (all that matters: < window)
+            const int z_left = z_left64 > kZWin ? kZWin : (int)z_left64;
             auto py_draw = [&](int k, bool active) -> double {  // the k-th unread U_py draw (for the lanes that take one)
                 if (!active) return 0.5;
-                if (py.i + pc + k >= py.e) err = 1;
+                if (pc + k >= py_left) err = 1;
                 return S_py[pc + k];
             };
 
@@ -399,7 +414,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 const int zk = __popc(surv & lt_mask);
                 double z = 0.5;
                 if (!dnf) {
-                    if (zz.i + zk >= zz.e) err = 1;
+                    if (zk >= z_left) err = 1;
                     z = S_z[zk];
                 }
                 zc = __popc(surv);
@@ -477,6 +492,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             }
             py.i += pc;
             zz.i += zc;
+#ifndef MCGP_REPLAY_LATE_FETCH
+            if (lap < L) fetch_windows();
+#endif
             update_positions(lap, lap <= drs_until, have_r, r);
         }
 
