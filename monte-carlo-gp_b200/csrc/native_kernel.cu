@@ -3,7 +3,7 @@
 // Behavioural source: reference src/simulation.py:59-560 (run_monte_carlo / simulate_race and the
 // handlers; each step below cites its lines).  What is B200-native here and absent upstream:
 //   * lane == driver index, so every per-driver parameter sits in a register for the whole launch;
-//   * draws come from Philox4x32-10 keyed by (seed; sim, lap pair, lane, stream): any sim range can be
+//   * draws come from Philox4x32-7 (native_math.cuh) keyed by (seed; sim, lap pair, lane, stream): any sim range can be
 //     launched on any GPU in any order and gives the same counts.  One call per lane serves TWO laps
 //     (a Box-Muller pair + 2 x 3 overtake uniforms); the otherwise idle lanes 20..31 supply the extra
 //     words and the race-event draws, so no lane computes Philox for nothing;
@@ -48,6 +48,8 @@ namespace mcgp {
 
 constexpr int kWarpsPerBlock = MCGP_WARPS_PER_BLOCK;
 constexpr int kThreads = kWarpsPerBlock * 32;
+// the lap-histogram variant runs ONE block per SM holding all resident warps (at most 32: 1024 threads per block)
+constexpr int kLapHistWarps = kWarpsPerBlock * MCGP_MIN_BLOCKS < 32 ? kWarpsPerBlock * MCGP_MIN_BLOCKS : 32;
 constexpr unsigned FULL = 0xffffffffu;
 
 // VSC tyre-age rollback probability 0.3 (src/simulation.py:392) as a 16-bit threshold
@@ -137,7 +139,7 @@ __device__ __forceinline__ float lt_one(float a, float b) {
 // so they rank behind every car in lane order; with NV4 == 5 only the first 20 keys are read and `park` (lane - 20
 // on lanes >= 20, else 0) completes their count.
 template <int NV4>
-__device__ __forceinline__ int rank_by_count(float t, float* S_t, int lane, int park) {
+__device__ __noinline__ int rank_by_count(float t, float* S_t, int lane, int park) {
     S_t[lane] = t;
     WARP_FENCE();
     const float4* v4 = reinterpret_cast<const float4*>(S_t);
@@ -188,7 +190,7 @@ struct NativeOutputs {
 // in shared memory (laps x n x n counters: 91 KB for 57 laps x 20 cars), so that variant runs ONE block of 32 warps
 // per SM where the others run four blocks of eight.
 template <int NV4, bool kExact, int kOut, int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, (MCGP_MIN_BLOCKS * MCGP_WARPS_PER_BLOCK) / kWarps)
+__global__ void __launch_bounds__(kWarps * 32, (MCGP_MIN_BLOCKS * MCGP_WARPS_PER_BLOCK) / kWarps > 0 ? (MCGP_MIN_BLOCKS * MCGP_WARPS_PER_BLOCK) / kWarps : 1)
 native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict__ ptab, const int pt_rows, const int pt_stride,  // ptab: PacePair tables, two pairs per uint4
                    unsigned long long n_sims, unsigned long long sim_begin,
                    const __grid_constant__ PhiloxKeys key, unsigned long long* __restrict__ hist,
@@ -749,7 +751,7 @@ static cudaError_t launch_out(int kout, const LaunchArgs& a) {
     if (kout == 0) return launch_one<NV4, kExact, 0, kWarpsPerBlock>(a);
     if (kout == 1) return launch_one<NV4, kExact, 1, kWarpsPerBlock>(a);
     if (kout == 2) return launch_one<NV4, kExact, 2, kWarpsPerBlock>(a);
-    return launch_one<NV4, kExact, 3, kWarpsPerBlock * MCGP_MIN_BLOCKS>(a);
+    return launch_one<NV4, kExact, 3, kLapHistWarps>(a);
 }
 
 int native_philox_rounds() { return MCGP_PHILOX_ROUNDS; }

@@ -1,4 +1,4 @@
-// Native-mode arithmetic: counter-based Philox4x32-10 and the two normal generators.
+// Native-mode arithmetic: counter-based Philox4x32-7 and the two normal generators.
 #pragma once
 #include <stdint.h>
 

@@ -121,8 +121,11 @@ __device__ __forceinline__ double py_sum_floats(const double* P, uint32_t items,
     return r;
 }
 
+#ifndef MCGP_REPLAY_MIN_BLOCKS
+#define MCGP_REPLAY_MIN_BLOCKS 6   // resident 128-thread blocks per SM the register budget is tuned for (80 registers: 17.8 M races/s; 5 blocks / 96 registers: 16.5 M)
+#endif
 template <int NP>
-__global__ void __launch_bounds__(kRThreads)
+__global__ void __launch_bounds__(kRThreads, MCGP_REPLAY_MIN_BLOCKS)
 replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sims, const double* __restrict__ u_py,
                    const double* __restrict__ zt, const double* __restrict__ u_np, const long long* __restrict__ off,
                    unsigned long long* __restrict__ hist, uint8_t* __restrict__ finish, double* __restrict__ times,
@@ -313,30 +316,20 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         }
 
         int drs_until = 0;
-        // The windows of lap l + 1 are fetched into registers at the END of lap l (the cursors are final once the
-        // overtake passes are through), so the loads fly under update_positions and only land in shared memory here.
-        double win_py[kPyWin / 32], win_z;
-        auto fetch_windows = [&]() {
+        for (int lap = 2; lap <= L; lap++) {
+            // ---- this lap's windows of the tapes: one coalesced refill, then shared-memory reads ----
+            // (tried: fetching the next lap's windows into registers at the end of the lap, under update_positions --
+            //  6 more registers and 8 % slower: the other warps already cover the one round trip per lap)
+            // pc / zc: draws of the window consumed so far.  A read past the end of the tape sets err (MCGP_ETAPE).
 #pragma unroll
             for (int w = 0; w < kPyWin / 32; w++) {
                 const long long q = py.i + 32 * w + lane;
-                win_py[w] = q < py.e ? py.p[q] : 0.5;
+                S_py[32 * w + lane] = q < py.e ? py.p[q] : 0.5;
             }
-            const long long q = zz.i + lane;
-            win_z = q < zz.e ? zz.p[q] : 0.5;
-        };
-#ifndef MCGP_REPLAY_LATE_FETCH
-        fetch_windows();
-#endif
-        for (int lap = 2; lap <= L; lap++) {
-#ifdef MCGP_REPLAY_LATE_FETCH
-            fetch_windows();
-#endif
-            // ---- this lap's windows of the tapes: one coalesced refill, then shared-memory reads ----
-            // pc / zc: draws of the window consumed so far.  A read past the end of the tape sets err (MCGP_ETAPE).
-#pragma unroll
-            for (int w = 0; w < kPyWin / 32; w++) S_py[32 * w + lane] = win_py[w];
-            S_z[lane] = win_z;
+            {
+                const long long q = zz.i + lane;
+                S_z[lane] = q < zz.e ? zz.p[q] : 0.5;
+            }
             __syncwarp();
             int pc = 0, zc = 0;
             const long long py_left64 = py.e - py.i, z_left64 = zz.e - zz.i;
@@ -492,9 +485,6 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             }
             py.i += pc;
             zz.i += zc;
-#ifndef MCGP_REPLAY_LATE_FETCH
-            if (lap < L) fetch_windows();
-#endif
             update_positions(lap, lap <= drs_until, have_r, r);
         }
 

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--workload", default="bahrain")
+    ap.add_argument("--mode", default="counts", choices=["counts", "trace", "laphist"],
+                    help="which kernel variant the timed launches use: count table only, + per-lap trace, + lap histogram")
     ap.add_argument("--tag", default=os.path.basename(os.environ.get("MCGP_LIB_PATH", "libmcgp.so")))
     args = ap.parse_args()
     import numpy as np
@@ -44,18 +46,32 @@ def main():
     n = p.n_drivers
     hist = torch.zeros((1, n, n), dtype=torch.int64, device="cuda:0")
     st = torch.cuda.current_stream().cuda_stream
+    laps = p.total_laps
+    extra = None
+    if args.mode == "trace":
+        extra = torch.empty(args.sims * laps * n * 8, dtype=torch.uint8, device="cuda:0")
+    elif args.mode == "laphist":
+        extra = torch.zeros((1, laps, n, n), dtype=torch.int64, device="cuda:0")
+
+    def launch(begin):
+        if args.mode == "trace":
+            eng.launch_native_traced(args.sims, begin, 42, hist.data_ptr(), extra.data_ptr(), 0, args.sims, stream=st)
+        elif args.mode == "laphist":
+            eng.launch_native_laphist(args.sims, begin, 42, hist.data_ptr(), extra.data_ptr(), stream=st)
+        else:
+            eng.launch_native(args.sims, begin, 42, hist.data_ptr(), stream=st)
     for _ in range(2):
-        eng.launch_native(args.sims, 0, 42, hist.data_ptr(), stream=st)
+        launch(0)
     torch.cuda.synchronize()
     best = 1e30
     for r in range(args.reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        eng.launch_native(args.sims, (r + 3) * args.sims, 42, hist.data_ptr(), stream=st)
+        launch((r + 3) * args.sims)
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b))
-    out.update(races_per_s=args.sims / (best * 1e-3), ms=best, sims=args.sims,
+    out.update(mode=args.mode, races_per_s=args.sims / (best * 1e-3), ms=best, sims=args.sims,
                hist_ok=int(hist.sum().item()) == (args.reps + 2) * args.sims * n)
     print(json.dumps(out))
 

@@ -1,4 +1,4 @@
-"""Native-mode CUDA path (Philox4x32-10, FP32) through the C ABI.
+"""Native-mode CUDA path (Philox4x32-7, FP32) through the C ABI.
 
 Three gates:
  1. logic, exactly: with the IEEE-only normal generator the kernel must reproduce the scalar CPU mirror
@@ -89,6 +89,27 @@ def test_native_statistics_high_power_fixed_grid(mcgp, oracle):
     assert abs(z["cells"][10, 1]) < 3.5 and abs(z["podium"][10]) < 3.5 and abs(z["podium"][2]) < 3.5
     zc = np.abs(z["cells"])
     assert zc.max() < 4.5 and (zc > 3).sum() <= 6 and np.abs(z["win"]).max() < 4.0 and np.abs(z["podium"]).max() < 4.0
+
+
+@pytest.mark.parametrize("case", ["bahrain_dry", "monaco_sc", "sprint19"])
+def test_native_statistics_high_power_baseline_workloads(mcgp, oracle, case):
+    """One high-power case per BASELINE workload (57-lap Bahrain, 78-lap Monaco with the high safety-car rate, the
+    19-lap sprint that exercises `pop` path B): 1e7 GPU sims against 1e6 reference sims, i.e. ~3x the resolution of
+    the two-stage 3-sigma cases above.  No relaxation for multiple comparisons beyond what chance needs: of ~440
+    statistics per case none may pass 4.5 sigma, win / podium none 4.0, at most 6 of 400 cells 3 sigma
+    (expected by chance: 1.1).  This is also the statistical gate of the 7-round Philox (native_math.cuh)."""
+    import stats_util as su
+    cfg, mc, seed, _ = gc.get_case(case)
+    sim = _sim(mcgp, cfg)
+    args = [mc.get(k) for k in MC_KEYS]
+    n_gpu, n_ref = 10_000_000, 1_000_000
+    got = sim.run_monte_carlo_counts(n_gpu, *args, seed=31337, track_condition=mc.get("track_condition", "dry"))
+    ref = oracle.run_monte_carlo(cfg, mc, n_ref, 777, *POP, threads=os.cpu_count() or 8)
+    z = su.compare_tables(got, n_gpu, ref, n_ref)
+    print(case, "high power:", su.summary(z))
+    zc = np.abs(z["cells"])
+    assert zc.max() < 4.5 and (zc > 3).sum() <= 6, su.summary(z)
+    assert np.abs(z["win"]).max() < 4.0 and np.abs(z["podium"]).max() < 4.0, su.summary(z)
 
 
 def test_fast_and_exact_normals_agree_statistically(mcgp):
