@@ -113,7 +113,8 @@ __device__ __forceinline__ double py_sum_floats(const double* P, uint32_t items,
     for (uint32_t m = items & (items - 1u); m; m &= m - 1u) {
         const double x = P[__ffs(m) - 1];
         const double t = r + x;
-        c += (fmax(r, x) - t) + fmin(r, x);
+        // every lane walks the same list, so this branch is warp-uniform (and almost always taken: r is a running sum)
+        if (r >= x) c += (r - t) + x; else c += (x - t) + r;
         r = t;
     }
     if (c != 0.0 && isfinite(c)) r += c;
@@ -137,12 +138,17 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     __shared__ __align__(16) double S_p_all[kRWarps][32];  // grid sampling items, then the rank keys
     __shared__ __align__(16) double S_c_all[kRWarps][32];  // running cumsum of the grid probabilities
-    __shared__ uint32_t S_inv_all[kRWarps][32];
+    __shared__ uint32_t S_inv_all[kRWarps][32];            // rank -> lane of the current all-cars order
+    // rank-indexed copies of what a car needs from its neighbours in the order (the car ahead's pace, time and last
+    // lap; the time at a run's start): one LDS each instead of a rank -> lane lookup plus two shuffles per double
+    __shared__ __align__(16) double S_cum_all[kRWarps][32];
+    __shared__ __align__(16) double S_op_all[kRWarps][32];
+    __shared__ __align__(16) double S_last_all[kRWarps][32];
     // Per-warp windows of the two lap-loop tapes, refilled once per lap with coalesced loads.  The draw sites of a lap
     // (events, retirement tests, noise, <= 3 overtake passes) depend on each other's outcome, so reading the tapes
     // from global memory where they are consumed cost 5-6 dependent DRAM/L2 round trips per lap (ncu r2b: 2.3 stall
     // cycles per issue on the long scoreboard, 14 % of all samples on the tape load); now it is one.
-    __shared__ __align__(16) double S_py_all[kRWarps][kPyWin];
+    __shared__ __align__(16) double S_py_all[kRWarps][kPyWin + 32];  // (+32: lanes that take no draw still index up to 31 past the cursor)
     __shared__ __align__(16) double S_z_all[kRWarps][kZWin];
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(race);
@@ -155,12 +161,16 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     double* S_p = S_p_all[warp];
     double* S_c = S_c_all[warp];
     uint32_t* S_inv = S_inv_all[warp];
+    double* S_cum = S_cum_all[warp];
+    double* S_op = S_op_all[warp];
+    double* S_last = S_last_all[warp];
     double* S_py = S_py_all[warp];
     double* S_z = S_z_all[warp];
     const int n = R.n, L = R.total_laps, track = R.track;
     const bool is_car = lane < n;
     const uint32_t nmask = n >= 32 ? RFULL : ((1u << n) - 1u);
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t lt_mask = (1u << lane) - 1u;
+    asm volatile("" : "+r"(lt_mask));  // (kept in a register: ptxas otherwise rebuilds it from SR_TID at each of its 14 uses per lap)
     int err = 0;
 
     // sims are claimed dynamically (counter host-initialised to the number of warps), one race ahead of their use:
@@ -252,7 +262,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         uint32_t used = 1u << comp;
         bool dnf = !is_car, drs = false;
         int dnf_lap = 0, pos_live = 0;
-        int lead = 0;  // lane of the leading runner as of the last update_positions (warp-uniform)
+        double t_lead = 0.0;  // time of the leading runner as of the last update_positions (warp-uniform)
         double cum = 0.0, last = 0.0, tbl = 0.0, ahead_last = 0.0;
 
         // _calculate_lap_time :313-332, strictly left to right
@@ -272,19 +282,20 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         auto update_positions = [&](int lap, bool drs_disabled, bool have_r, int r_all) {
             if (!have_r) {
                 r_all = rank_set<NP>(cum, nmask, lane, S_p);
-                __syncwarp();
-                if (is_car) S_inv[r_all] = lane;
-                __syncwarp();
+                if (is_car) { S_inv[r_all] = lane; S_cum[r_all] = cum; }
             }
-            const uint32_t LM = __reduce_or_sync(RFULL, (is_car && !dnf) ? (1u << r_all) : 0u);  // ranks held by runners
+            if (is_car) S_last[r_all] = last;
+            __syncwarp();
+            const bool runner = is_car && !dnf;
+            const uint32_t LM = __reduce_or_sync(RFULL, runner ? (1u << r_all) : 0u);  // ranks held by runners
             if (LM) {
-                lead = (int)S_inv[__ffs(LM) - 1];
-                const uint32_t below = (is_car && !dnf) ? (LM & ((1u << r_all) - 1u)) : 0u;
-                const int pl = below ? (int)S_inv[31 - __clz(below)] : lane;
-                const double t0 = shfl_d(cum, lead), tp = shfl_d(cum, pl), lp = shfl_d(last, pl);
+                t_lead = S_cum[__ffs(LM) - 1];
+                const uint32_t below = runner ? (LM & ((1u << r_all) - 1u)) : 0u;
+                const int pr = below ? 31 - __clz(below) : (r_all & 31);   // rank of the runner ahead (own rank: unused)
+                const double tp = S_cum[pr], lp = S_last[pr];
                 if (!dnf) {
                     pos_live = __popc(below);
-                    tbl = cum - t0;
+                    tbl = cum - t_lead;
                     if (lap <= 2 || drs_disabled || pos_live == 0) drs = false;
                     else drs = (cum - tp) < 1.0;
                     ahead_last = pos_live > 0 ? lp : 0.0;
@@ -335,11 +346,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             const long long py_left64 = py.e - py.i, z_left64 = zz.e - zz.i;
             const int py_left = py_left64 > kPyWin ? kPyWin : (int)py_left64;  // draws left on the tape (all that matters: < window)
             const int z_left = z_left64 > kZWin ? kZWin : (int)z_left64;
-            auto py_draw = [&](int k, bool active) -> double {  // the k-th unread U_py draw (for the lanes that take one)
-                if (!active) return 0.5;
-                if (pc + k >= py_left) err = 1;
-                return S_py[pc + k];
-            };
+            // the k-th unread U_py draw: a plain window read (k <= 31, so the index stays inside the window; entries past
+            // the end of the tape hold 0.5).  Whether the lap consumed more than the tape had left is checked once, below.
+            auto py_draw = [&](int k, bool) -> double { return S_py[pc + k]; };
 
             // ---- events :168-176 (short-circuit draws) ------------------------------------------
             int ev = 0;
@@ -358,7 +367,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             if (ev) {
                 const uint32_t live_m = __ballot_sync(RFULL, !dnf);
                 if (live_m) {
-                    const double t0 = shfl_d(cum, lead);  // still the leader of the last update_positions
+                    const double t0 = t_lead;  // the leader's time as of the last update_positions (nothing moved since)
                     const int rem = L - lap;
                     if (ev == 1) {  // _handle_red_flag :397-431
                         if (!dnf) {
@@ -405,11 +414,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 if (was_live && u < dnf_rate) { dnf = true; dnf_lap = lap; }
                 const uint32_t surv = __ballot_sync(RFULL, !dnf);
                 const int zk = __popc(surv & lt_mask);
-                double z = 0.5;
-                if (!dnf) {
-                    if (zk >= z_left) err = 1;
-                    z = S_z[zk];
-                }
+                const double z = S_z[zk];
                 zc = __popc(surv);
                 if (!dnf) {
                     const double clean = lap_time(lap, z);
@@ -445,21 +450,35 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             }
 
             // ---- _simulate_overtakes :496-536 --------------------------------------------------
-            bool have_r = false;  // r / S_inv below describe the current times (the last pass changed nothing)
+            bool have_r = false;  // r / S_inv / S_cum below describe the current times (the last pass changed nothing)
             int r = 0;
             {
                 const double op = R.pace[drv] + (double)age * deg;  // :514-515 (raw driver deg)
+                const double op_pub = dnf ? __longlong_as_double(0x7ff8000000000000ll) : op;  // NaN: a retired car blocks its pairs (Q5)
+                bool guessed = false;  // r is the previous order with every run of successes reversed: verified below
                 for (int pass = 0; pass < 3; pass++) {
-                    r = rank_set<NP>(cum, nmask, lane, S_p);  // ALL cars, retired ones included (Q5)
+                    if (!guessed) r = rank_set<NP>(cum, nmask, lane, S_p);  // ALL cars, retired ones included (Q5)
+                    if (is_car) { S_inv[r] = lane; S_cum[r] = cum; S_op[r] = op_pub; }
                     __syncwarp();
-                    if (is_car) S_inv[r] = lane;
-                    __syncwarp();
-                    const int la = (is_car && r > 0) ? (int)S_inv[r - 1] : lane;
-                    const double op_a = shfl_d(op, la);
-                    const bool dnf_a = __shfl_sync(RFULL, (int)dnf, la) != 0;
-                    double delta = op_a - op;
+                    if (guessed) {
+                        // The re-written times descend by 0.1 s inside a run, so the new order is almost always the old one
+                        // with each run reversed; it is THE order iff (time, grid slot) increases strictly along it.
+                        bool ok = true;
+                        if (is_car && r > 0) {
+                            const double c_prev = S_cum[r - 1];
+                            ok = c_prev < cum || (c_prev == cum && (int)S_inv[r - 1] < lane);
+                        }
+                        if (!__all_sync(RFULL, ok)) {
+                            __syncwarp();
+                            r = rank_set<NP>(cum, nmask, lane, S_p);
+                            if (is_car) { S_inv[r] = lane; S_cum[r] = cum; S_op[r] = op_pub; }
+                            __syncwarp();
+                        }
+                    }
+                    const double op_a = S_op[(r > 0 ? r - 1 : 0) & 31];
+                    double delta = op_a - op;   // NaN if the car ahead is retired: every comparison below is false
                     if (drs) delta += R.drs_delta;
-                    const bool cond = is_car && r > 0 && !dnf && !dnf_a && delta > R.ovt_delta;
+                    const bool cond = is_car && r > 0 && !dnf && delta > R.ovt_delta;
                     const uint32_t CM = __reduce_or_sync(RFULL, cond ? (1u << r) : 0u);
                     const double u = py_draw(__popc(CM & ((1u << r) - 1u)), cond);  // draws in sorted order :524
                     pc += __popc(CM);
@@ -467,22 +486,25 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     if (prob > 0.5) prob = 0.5;
                     const bool succ = cond && u < prob;
                     const uint32_t M = __reduce_or_sync(RFULL, succ ? (1u << r) : 0u);
-                    if (M == 0u) { have_r = true; __syncwarp(); break; }
+                    if (M == 0u) { have_r = true; break; }
                     // sequential re-write chain :528-530, replayed op by op for bit-exactness
                     const uint32_t clear_below = ~M & ((2u << r) - 1u);
                     const int j = 31 - __clz(clear_below);
                     const int k = is_car ? r - j : 0;
-                    const int lj = is_car ? (int)S_inv[j] : lane;
-                    double a = shfl_d(cum, lj);
+                    double a = S_cum[j & 31];
                     const int sn = is_car ? (int)(((M >> r) >> 1) & 1u) : 0;
                     const int steps = k + sn;
                     const int max_steps = __reduce_max_sync(RFULL, steps);
                     for (int q = 0; q < max_steps; q++)
                         if (q < steps) { a = a - 0.1; if (!(a > 0.1)) a = 0.1; }  // max(0.1, ahead - 0.1)
                     if (steps > 0) cum = sn ? a + 0.3 : a;
+                    // presumed order for the next pass: every run [j, e] reversed
+                    if (is_car) r = j + __ffs(~((M >> r) >> 1)) - 1;   // j + e - r with e = r + (successes right behind this car)
+                    guessed = true;
                     __syncwarp();
                 }
             }
+            if (pc > py_left || zc > z_left) err = 1;  // the lap read past the end of a tape (MCGP_ETAPE)
             py.i += pc;
             zz.i += zc;
             update_positions(lap, lap <= drs_until, have_r, r);

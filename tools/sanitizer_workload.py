@@ -56,4 +56,9 @@ out = sim.replay(mc["grid_probs"], mc["base_pace"], mc["tire_deg"], mc["driver_v
                  u_py=rng.random(ns * per[0]), z=rng.standard_normal(ns * per[1]), u_np=rng.random(ns * per[2]),
                  offsets=off.astype(np.int64))
 assert out["finish"].shape == (ns, 20)
+# lap-histogram variant (one 32-warp block per SM), on-device scoring, the device-resident season loop
+h, lh = eng.run_native_laphist([p], n, 0, 42)
+assert int(lh[0, 0].sum()) <= n * 20
+season = m.season.run_device_season(max(200, n // 10), 5, races=[0, 1, 2], pop_no_medium="SOFT", pop_no_soft="MEDIUM")
+assert season["hist"].shape == (3, 20, 20)
 print("sanitizer workload ok:", n, "native sims per variant,", ns, "replay sims")
