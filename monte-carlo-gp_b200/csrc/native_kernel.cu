@@ -579,6 +579,8 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 sts_f<0>(wa, t);
                 XCHG_FENCE();
                 const float a1 = lds_f<-4>(wa), a2 = lds_f<-8>(wa), b1 = lds_f<4>(wa), b2 = lds_f<8>(wa);
+                // (tried: integer masks added with IADD3 instead of FSET.BF + FADD + F2I -- `set.lt.s32.f32` compiles to
+                //  FSETP + SEL on sm_100, one instruction more per neighbour)
                 const float moved = (lt_one(b1, t) + lt_one(b2, t)) - (lt_one(t, a1) + lt_one(t, a2));
                 set_rank(rank + (int)moved);
                 // (no fence needed here: REC was last READ before the fence above, W is not written again in this call)
@@ -589,9 +591,9 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 have_rank = cover == FULL && !__any_sync(FULL, !(prev.x < t));
             };
             window_place();  // first ordering of the lap
+            if (!have_rank) full_rank(op32);  // (from here on rank / prev always describe the current times)
             // one pass; returns true when another pass may follow
             auto one_pass = [&](const uint32_t u16) -> bool {
-                if (!have_rank) full_rank(op32);
                 const float delta = __fadd_rn(prev.y, -opb);  // pace_ahead - pace_behind (+ drs_delta), x 2^15
                 // u16 * 2^-16 < min(0.5, delta / 2)   <=>   u16 < min(32768, delta * 32768)   (exact scaling); a retired
                 // car on either side makes delta NaN, the NaN-propagating min keeps it and the compare fails (Q5)
@@ -619,12 +621,14 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 XCHG_FENCE();
                 prev = lds_f2<-8>(ra);
                 have_rank = !__any_sync(FULL, !(prev.x < t));
-                if (!have_rank) window_place();  // second chance before counting all ranks
+                if (!have_rank) {
+                    window_place();  // second chance before counting all ranks
+                    if (!have_rank) full_rank(op32);
+                }
                 return true;
             };
             if (one_pass(u12 & 0xffffu))
                 if (one_pass(u12 >> 16)) one_pass(odd ? ext >> 16 : ext & 0xffffu);
-            if (!have_rank) full_rank(op32);
             update_positions(lap, dnf);
             emit_trace(lap, dnf);
             count_lap(lap, dnf);

@@ -107,11 +107,13 @@ __device__ double py_sum(const double* P, const uint8_t* K, int n, int& result_k
 // The same sum() when every item is an exact float or an int 0 (`items`: lanes whose item is a float; warp-uniform):
 // int zeros add 0.0 to a non-negative partial sum (a no-op), so only the float items are visited, in index order, and
 // with non-negative terms Neumaier's branch `abs(r) >= abs(x)` is max / min.  Bit-identical to py_sum on such lists.
-__device__ __forceinline__ double py_sum_floats(const double* P, uint32_t items, int& result_kind) {
-    if (items == 0u) { result_kind = 0; return 0.0; }
-    double r = 0.0 + P[__ffs(items) - 1], c = 0.0;
-    for (uint32_t m = items & (items - 1u); m; m &= m - 1u) {
-        const double x = P[__ffs(m) - 1];
+// D: the float items compacted in index order (D[k] = k-th float item), cnt of them.
+__device__ __forceinline__ double py_sum_floats(const double* D, int cnt, int& result_kind) {
+    if (cnt == 0) { result_kind = 0; return 0.0; }
+    double r = 0.0 + D[0], c = 0.0;
+#pragma unroll 4
+    for (int i = 1; i < cnt; i++) {
+        const double x = D[i];
         const double t = r + x;
         // every lane walks the same list, so this branch is warp-uniform (and almost always taken: r is a running sum)
         if (r >= x) c += (r - t) + x; else c += (x - t) + r;
@@ -136,20 +138,24 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     constexpr int kPyWin = NP == 10 ? 96 : 160, kZWin = 32;
     __shared__ ReplayRace R;
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
-    __shared__ __align__(16) double S_p_all[kRWarps][32];  // grid sampling items, then the rank keys
-    __shared__ __align__(16) double S_c_all[kRWarps][32];  // running cumsum of the grid probabilities
-    __shared__ uint32_t S_inv_all[kRWarps][32];            // rank -> lane of the current all-cars order
-    // rank-indexed copies of what a car needs from its neighbours in the order (the car ahead's pace, time and last
-    // lap; the time at a run's start): one LDS each instead of a rank -> lane lookup plus two shuffles per double
-    __shared__ __align__(16) double S_cum_all[kRWarps][32];
-    __shared__ __align__(16) double S_op_all[kRWarps][32];
-    __shared__ __align__(16) double S_last_all[kRWarps][32];
-    // Per-warp windows of the two lap-loop tapes, refilled once per lap with coalesced loads.  The draw sites of a lap
-    // (events, retirement tests, noise, <= 3 overtake passes) depend on each other's outcome, so reading the tapes
-    // from global memory where they are consumed cost 5-6 dependent DRAM/L2 round trips per lap (ncu r2b: 2.3 stall
-    // cycles per issue on the long scoreboard, 14 % of all samples on the tape load); now it is one.
-    __shared__ __align__(16) double S_py_all[kRWarps][kPyWin + 32];  // (+32: lanes that take no draw still index up to 31 past the cursor)
-    __shared__ __align__(16) double S_z_all[kRWarps][kZWin];
+    // Everything a warp exchanges through shared memory sits in ONE struct per warp, addressed from one pinned base
+    // pointer with compile-time offsets (as eight separate arrays ptxas re-derived each array's address from the warp
+    // index at every use to save registers: 8 % of all executed instructions, ncu r2m).
+    struct WarpScratch {
+        double p[32];              // grid sampling items, then the rank keys
+        double c[32];              // running cumsum of the grid probabilities (first bytes: item kinds on the general sum() path)
+        // rank-indexed copies of what a car needs from its neighbours in the order (the car ahead's pace, time and last
+        // lap; the time at a run's start): one LDS each instead of a rank -> lane lookup plus two shuffles per double
+        double cum[32], op[32], last[32];
+        // Per-warp windows of the two lap-loop tapes, refilled once per lap with coalesced loads.  The draw sites of a lap
+        // (events, retirement tests, noise, <= 3 overtake passes) depend on each other's outcome, so reading the tapes
+        // from global memory where they are consumed cost 5-6 dependent DRAM/L2 round trips per lap (ncu r2b: 2.3 stall
+        // cycles per issue on the long scoreboard, 14 % of all samples on the tape load); now it is one.
+        double py[kPyWin + 32];    // (+32: lanes that take no draw still index up to 31 past the cursor)
+        double z[kZWin];
+        uint32_t inv[32];          // rank -> lane of the current all-cars order
+    };
+    __shared__ __align__(16) WarpScratch scratch[kRWarps];
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(race);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&R);
@@ -158,14 +164,16 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* S_p = S_p_all[warp];
-    double* S_c = S_c_all[warp];
-    uint32_t* S_inv = S_inv_all[warp];
-    double* S_cum = S_cum_all[warp];
-    double* S_op = S_op_all[warp];
-    double* S_last = S_last_all[warp];
-    double* S_py = S_py_all[warp];
-    double* S_z = S_z_all[warp];
+    WarpScratch* ws = &scratch[warp];
+    asm volatile("" : "+l"(ws));   // one live base pointer; every array below is a constant offset from it
+    double* const S_p = ws->p;
+    double* const S_c = ws->c;
+    uint32_t* const S_inv = ws->inv;
+    double* const S_cum = ws->cum;
+    double* const S_op = ws->op;
+    double* const S_last = ws->last;
+    double* const S_py = ws->py;
+    double* const S_z = ws->z;
     const int n = R.n, L = R.total_laps, track = R.track;
     const bool is_car = lane < n;
     const uint32_t nmask = n >= 32 ? RFULL : ((1u << n) - 1u);
@@ -195,14 +203,16 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 uint8_t kd = 0;
                 double pd = 0.0;
                 if (is_car && ((remaining >> lane) & 1u) && R.kind[lane][pos] != 0) { pd = R.grid[lane][pos]; kd = R.kind[lane][pos]; }
-                S_p[lane] = pd;
                 const uint32_t m_float = __ballot_sync(RFULL, kd == 1), m_np = __ballot_sync(RFULL, kd == 2);
-                __syncwarp();
                 int tk;
                 double total;  // :123
-                if (m_np == 0u) {
-                    total = py_sum_floats(S_p, m_float, tk);
+                if (m_np == 0u) {  // floats and int zeros only: the float items, compacted in driver order
+                    if (kd == 1) S_c[__popc(m_float & lt_mask)] = pd;
+                    __syncwarp();
+                    total = py_sum_floats(S_c, __popc(m_float), tk);
                 } else {  // np.float64 items: CPython's sum() leaves its compensated loop (Q12) -- the general state machine
+                    S_p[lane] = pd;
+                    __syncwarp();
                     uint8_t* S_k = reinterpret_cast<uint8_t*>(S_c);
                     S_k[lane] = kd;
                     __syncwarp();
