@@ -214,6 +214,13 @@ int mcgp_run_replay(mcgp_handle h, const mcgp_race_params* race, uint64_t n_sims
                     const double* z, const double* u_np, const int64_t* off, uint64_t* hist_host,
                     uint8_t* finish_host, double* times_host, int16_t* dnf_lap_host, uint8_t* grid_host,
                     int64_t* used_host);
+/* _sample_grid in replay mode (src/simulation.py:102-145): the kernel evaluates each grid position's selection with a
+ * warp scan and accepts it only where that provably equals the reference's serial evaluation (CPython sum(), division,
+ * NumPy cumsum, searchsorted: every intermediate within (n + 4) ulp of the scan, the draw farther than 1e-12 from every
+ * boundary); everything else -- about one position in 1e11, rows with negative or non-finite items, all-zero rows --
+ * takes the serial evaluation in the reference's operation order.  on != 0 sends EVERY position down the serial path
+ * (verification of the above: both settings must give identical grids); default 0.  Applies to later launches. */
+int mcgp_replay_serial_grid(mcgp_handle h, int on);
 /* Device-resident form (tapes and outputs are device pointers; race block from mcgp_upload_races). */
 int mcgp_launch_replay(mcgp_handle h, uint64_t n_sims, const double* u_py_dev, const double* z_dev,
                        const double* u_np_dev, const int64_t* off_dev, uint64_t* hist_dev,

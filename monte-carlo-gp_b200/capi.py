@@ -83,6 +83,7 @@ _SIGNATURES = {
                                   C.c_double] + [C.c_void_p] * 14),
     "mcgp_run_replay": (C.c_int, [C.c_void_p, C.POINTER(McgpRaceParams), C.c_uint64] + [C.c_void_p] * 10),
     "mcgp_launch_replay": (C.c_int, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 12),
+    "mcgp_replay_serial_grid": (C.c_int, [C.c_void_p, C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -270,6 +271,11 @@ class Engine:
             _p(out.get("times")), _p(out.get("dnf_lap")), _p(out.get("grid")), _p(out.get("used"))))
         self.n_races, self.n_drivers = 1, n
         return out
+
+    def replay_serial_grid(self, on: bool):
+        """Send every _sample_grid position of later replay launches down the serial (reference operation order) path;
+        by default the kernel takes it only where its parallel evaluation cannot certify the same selection."""
+        self._check(self._lib.mcgp_replay_serial_grid(self._h, 1 if on else 0))
 
     def launch_replay(self, n_sims, u_py_ptr, z_ptr, u_np_ptr, off_ptr, hist_ptr, finish_ptr=None, times_ptr=None,
                       dnf_lap_ptr=None, grid_ptr=None, used_ptr=None, status_ptr=None, stream=None):

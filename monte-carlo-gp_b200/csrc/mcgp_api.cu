@@ -23,7 +23,7 @@ cudaError_t launch_native(const NativeRace* races_dev, const PacePair* pace_dev,
 cudaError_t launch_replay(const ReplayRace* race_dev, int n_drivers, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
-                          unsigned long long* work_counter, int sm_count, cudaStream_t st);
+                          unsigned long long* work_counter, int sm_count, cudaStream_t st, bool serial_grid);
 cudaError_t launch_season_grid(NativeRace* race_dev, const double* quali_dev, const int32_t* penalty_dev, const double* teammate_dev,
                                const double* form_dev, const double* circuit_dev, int n, double* rows_dev, cudaStream_t st);
 cudaError_t launch_season_elo(const uint8_t* grid_order, const uint8_t* finish_order, const double* q_before, const double* r_before,
@@ -51,6 +51,7 @@ struct mcgp_context {
     int n_races = 0, n_drivers = 0;    // the uploaded batch; n_races == 0: nothing (valid) is resident
     bool replay_ready = false;         // replay_dev holds the blocks of the resident batch (derived lazily, see ensure_replay)
     bool uniform_laps = true;          // every race of the resident batch has the same total_laps
+    bool replay_serial_grid = false;   // mcgp_replay_serial_grid: every _sample_grid position on the serial path
     int launches = 0;
     uint64_t upload_bytes = 0;
     std::vector<mcgp_race_params> resident;  // host copy of the resident batch: a repeated call with identical
@@ -761,6 +762,12 @@ int mcgp_run_season(mcgp_handle h, const mcgp_race_params* races, int n_races, u
     return MCGP_OK;
 }
 
+int mcgp_replay_serial_grid(mcgp_handle h, int on) {
+    if (!h) return MCGP_EINVAL;
+    h->replay_serial_grid = on != 0;
+    return MCGP_OK;
+}
+
 int mcgp_launch_replay(mcgp_handle h, uint64_t n_sims, const double* u_py_dev, const double* z_dev, const double* u_np_dev,
                        const int64_t* off_dev, uint64_t* hist_dev, uint8_t* finish_dev, double* times_dev,
                        int16_t* dnf_lap_dev, uint8_t* grid_dev, int64_t* used_dev, int32_t* status_dev, void* cuda_stream) {
@@ -778,7 +785,7 @@ int mcgp_launch_replay(mcgp_handle h, uint64_t n_sims, const double* u_py_dev, c
     CU(order_before(h, st));
     CU(mcgp::launch_replay(h->replay_dev, h->n_drivers, n_sims, u_py_dev, z_dev, u_np_dev, (const long long*)off_dev,
                            (unsigned long long*)hist_dev, finish_dev, times_dev, dnf_lap_dev, grid_dev,
-                           (long long*)used_dev, status_dev, h->work_counter, h->sm_count, st));
+                           (long long*)used_dev, status_dev, h->work_counter, h->sm_count, st, h->replay_serial_grid));
     CU(order_after(h, st));
     h->launches = 2;  // the claim-counter reset + the replay kernel
     return MCGP_OK;

@@ -124,6 +124,66 @@ __device__ __forceinline__ double py_sum_floats(const double* D, int cnt, int& r
     return r;
 }
 
+// One grid position of _sample_grid (:119-139) evaluated serially, in the reference's operation order: CPython's sum()
+// (py_sum / py_sum_floats), the division, the 1e-9 renormalisation test, NumPy's left-to-right cumsum, the division by
+// its last element, searchsorted(u, side='right').  lane d holds driver d's item (pd, kind kd).  Out of line: the
+// kernel takes this path only where the parallel evaluation cannot certify the selection (see the call site).
+__device__ __noinline__ int sample_slot_serial(double* S_p, double* S_c, double pd, uint8_t kd, uint32_t remaining, int n, int lane, double u) {
+    const bool is_car = lane < n;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t m_float = __ballot_sync(RFULL, kd == 1), m_np = __ballot_sync(RFULL, kd == 2);
+    int tk;
+    double total;  // :123
+    if (m_np == 0u) {  // floats and int zeros only: the float items, compacted in driver order
+        if (kd == 1) S_c[__popc(m_float & lt_mask)] = pd;
+        __syncwarp();
+        total = py_sum_floats(S_c, __popc(m_float), tk);
+    } else {  // np.float64 items: CPython's sum() leaves its compensated loop (Q12) -- the general state machine
+        S_p[lane] = pd;
+        __syncwarp();
+        uint8_t* S_k = reinterpret_cast<uint8_t*>(S_c);
+        S_k[lane] = kd;
+        __syncwarp();
+        total = py_sum(S_p, S_k, n, tk);
+    }
+    __syncwarp();
+    if (total > 0) {  // :125-126
+        pd = pd / total;
+        kd = (tk == 2 || kd == 2) ? 2 : 1;
+    } else {  // :127-130
+        const int n_rem = __popc(remaining);
+        if ((remaining >> lane) & 1u) { pd = 1.0 / (double)n_rem; kd = 1; } else { pd = 0.0; kd = 0; }
+    }
+    // :133-135 renormalise if abs(sum(probs) - 1) > 1e-9.  The exact sum() only matters when that fires:
+    // a butterfly sum is within ~1e-15 of it, so unless it lands near the threshold the (usual) answer
+    // "no renormalisation" is certain without replaying CPython's serial summation.
+    double approx = pd;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) approx += shfl_d(approx, lane ^ d);
+    if (!__all_sync(RFULL, fabs(approx - 1.0) < 1e-9 - 1e-12)) {
+        uint8_t* S_k = reinterpret_cast<uint8_t*>(S_c);
+        S_p[lane] = pd; S_k[lane] = kd;
+        __syncwarp();
+        const double prob_sum = py_sum(S_p, S_k, n, tk);  // :133
+        __syncwarp();
+        if (prob_sum > 0 && fabs(prob_sum - 1.0) > 1e-9) pd = pd / prob_sum;  // :134-135
+    }
+    S_p[lane] = pd;
+    __syncwarp();
+    // p.cumsum(); cdf /= cdf[-1]; searchsorted(u, side='right').  cumsum is a serial left-to-right loop:
+    // every lane runs it, the running sums go through shared memory and each lane picks up its own.
+    double acc = S_p[0];
+    S_c[0] = acc;
+#pragma unroll 4
+    for (int d = 1; d < n; d++) { acc = acc + S_p[d]; S_c[d] = acc; }
+    __syncwarp();
+    const double cdf = (is_car ? S_c[lane] : acc) / acc;
+    __syncwarp();
+    int sel = __popc(__ballot_sync(RFULL, is_car && cdf <= u));
+    if (sel > n - 1) sel = n - 1;
+    return sel;
+}
+
 #ifndef MCGP_REPLAY_MIN_BLOCKS
 #define MCGP_REPLAY_MIN_BLOCKS 6   // resident 128-thread blocks per SM the register budget is tuned for (80 registers: 17.8 M races/s; 5 blocks / 96 registers: 16.5 M)
 #endif
@@ -133,7 +193,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                    const double* __restrict__ zt, const double* __restrict__ u_np, const long long* __restrict__ off,
                    unsigned long long* __restrict__ hist, uint8_t* __restrict__ finish, double* __restrict__ times,
                    int16_t* __restrict__ dnf_lap_out, uint8_t* __restrict__ grid_out, long long* __restrict__ used_out,
-                   int* __restrict__ status, unsigned long long* __restrict__ work_counter) {
+                   int* __restrict__ status, unsigned long long* __restrict__ work_counter, const int serial_grid) {
     // draws one lap can consume at most: 4 event draws + n retirement tests + 3 passes x (n - 1) pairs (U_py), n normals (Z)
     constexpr int kPyWin = NP == 10 ? 96 : 160, kZWin = 32;
     __shared__ ReplayRace R;
@@ -147,6 +207,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         // rank-indexed copies of what a car needs from its neighbours in the order (the car ahead's pace, time and last
         // lap; the time at a run's start): one LDS each instead of a rank -> lane lookup plus two shuffles per double
         double cum[32], op[32], last[32];
+        double win[36];            // first ordering of a lap: the new times by OLD rank between -inf / +inf pads (win[2 + rank])
         // Per-warp windows of the two lap-loop tapes, refilled once per lap with coalesced loads.  The draw sites of a lap
         // (events, retirement tests, noise, <= 3 overtake passes) depend on each other's outcome, so reading the tapes
         // from global memory where they are consumed cost 5-6 dependent DRAM/L2 round trips per lap (ncu r2b: 2.3 stall
@@ -174,6 +235,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     double* const S_last = ws->last;
     double* const S_py = ws->py;
     double* const S_z = ws->z;
+    double* const W = ws->win + 2;
+    for (int i = lane; i < 36; i += 32) ws->win[i] = __longlong_as_double(i < 2 ? 0xfff0000000000000ll : 0x7ff0000000000000ll);
+    __syncwarp();
     const int n = R.n, L = R.total_laps, track = R.track;
     const bool is_car = lane < n;
     const uint32_t nmask = n >= 32 ? RFULL : ((1u << n) - 1u);
@@ -203,57 +267,29 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 uint8_t kd = 0;
                 double pd = 0.0;
                 if (is_car && ((remaining >> lane) & 1u) && R.kind[lane][pos] != 0) { pd = R.grid[lane][pos]; kd = R.kind[lane][pos]; }
-                const uint32_t m_float = __ballot_sync(RFULL, kd == 1), m_np = __ballot_sync(RFULL, kd == 2);
-                int tk;
-                double total;  // :123
-                if (m_np == 0u) {  // floats and int zeros only: the float items, compacted in driver order
-                    if (kd == 1) S_c[__popc(m_float & lt_mask)] = pd;
-                    __syncwarp();
-                    total = py_sum_floats(S_c, __popc(m_float), tk);
-                } else {  // np.float64 items: CPython's sum() leaves its compensated loop (Q12) -- the general state machine
-                    S_p[lane] = pd;
-                    __syncwarp();
-                    uint8_t* S_k = reinterpret_cast<uint8_t*>(S_c);
-                    S_k[lane] = kd;
-                    __syncwarp();
-                    total = py_sum(S_p, S_k, n, tk);
-                }
-                __syncwarp();
-                if (total > 0) {  // :125-126
-                    pd = pd / total;
-                    kd = (tk == 2 || kd == 2) ? 2 : 1;
-                } else {  // :127-130
-                    const int n_rem = __popc(remaining);
-                    if ((remaining >> lane) & 1u) { pd = 1.0 / (double)n_rem; kd = 1; } else { pd = 0.0; kd = 0; }
-                }
-                // :133-135 renormalise if abs(sum(probs) - 1) > 1e-9.  The exact sum() only matters when that fires:
-                // a butterfly sum is within ~1e-15 of it, so unless it lands near the threshold the (usual) answer
-                // "no renormalisation" is certain without replaying CPython's serial summation.
-                double approx = pd;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) approx += shfl_d(approx, lane ^ d);
-                if (!__all_sync(RFULL, fabs(approx - 1.0) < 1e-9 - 1e-12)) {
-                    uint8_t* S_k = reinterpret_cast<uint8_t*>(S_c);
-                    S_p[lane] = pd; S_k[lane] = kd;
-                    __syncwarp();
-                    const double prob_sum = py_sum(S_p, S_k, n, tk);  // :133
-                    __syncwarp();
-                    if (prob_sum > 0 && fabs(prob_sum - 1.0) > 1e-9) pd = pd / prob_sum;  // :134-135
-                }
-                S_p[lane] = pd;
-                __syncwarp();
-                // p.cumsum(); cdf /= cdf[-1]; searchsorted(u, side='right').  cumsum is a serial left-to-right loop:
-                // every lane runs it, the running sums go through shared memory and each lane picks up its own.
-                double acc = S_p[0];
-                S_c[0] = acc;
-#pragma unroll 4
-                for (int d = 1; d < n; d++) { acc = acc + S_p[d]; S_c[d] = acc; }
-                __syncwarp();
-                const double cdf = (is_car ? S_c[lane] : acc) / acc;
-                __syncwarp();
                 const double u = shfl_d(u_mine, pos);
-                int sel = __popc(__ballot_sync(RFULL, is_car && cdf <= u));
-                if (sel > n - 1) sel = n - 1;
+                // What :123-137 compute is  sel = #{i : cdf_i <= u}  with cdf = cumsum(p / sum(p)) / cumsum(...)[-1]: a DISCRETE
+                // result.  With non-negative items every intermediate of the reference's serial evaluation (CPython's
+                // compensated sum(), the division, NumPy's left-to-right cumsum, the final division) is within (n + 4) ulp
+                // < 1e-14 of the true F_i = sum_{j<=i} p_j / sum_j p_j, and so is a warp scan of the raw items divided by its
+                // last element.  So: scan the items (5 shuffle steps), compare prefix_i with u x total, and accept the count
+                // when no prefix is within 1e-12 x total of the threshold -- the serial evaluation then provably selects the
+                // same driver.  Otherwise (once in ~1e11 draws; negative / non-finite items; an all-zero row, :127-130)
+                // the position is evaluated serially in the reference's operation order (sample_slot_serial).
+                double pre = pd;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double v = __shfl_up_sync(RFULL, pre, d);
+                    if (lane >= d) pre += v;
+                }
+                const double tot = shfl_d(pre, 31);
+                const double diff = pre - u * tot;
+                const bool certain = pd >= 0.0 && (!is_car || fabs(diff) > 1e-12 * tot);   // (NaN anywhere: not certain)
+                int sel;
+                if (!serial_grid && tot > 1e-280 && tot < 1e280 && __all_sync(RFULL, certain))
+                    sel = __popc(__ballot_sync(RFULL, is_car && diff <= 0.0));
+                else
+                    sel = sample_slot_serial(S_p, S_c, pd, kd, remaining, n, lane, u);
                 if (lane == pos) drv = sel;
                 remaining &= ~(1u << sel);  // :139
             }
@@ -289,7 +325,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         // _update_positions :538-560.  r_all: this car's rank among ALL cars by (time, grid slot) with S_inv the matching
         // rank -> lane map -- the order the last overtake pass worked on when it changed nothing (have_r), else derived
         // here.  The live order is its restriction to the runners (same tie-break), so no second sort is needed.
-        auto update_positions = [&](int lap, bool drs_disabled, bool have_r, int r_all) {
+        auto update_positions = [&](int lap, bool drs_disabled, bool have_r, int& r_all) {
             if (!have_r) {
                 r_all = rank_set<NP>(cum, nmask, lane, S_p);
                 if (is_car) { S_inv[r_all] = lane; S_cum[r_all] = cum; }
@@ -314,6 +350,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             __syncwarp();
         };
 
+        // r: this car's rank among ALL cars by (time, grid slot) as of the last update_positions -- the guess the next
+        // lap's first ordering starts from
+        int r = 0;
         // ---- _simulate_lap_1 (:275-311) --------------------------------------------------------
         {
             const double u = py.at(lane, is_car, err);
@@ -333,7 +372,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 cum += lt;
                 age += 1;
             }
-            update_positions(1, true, false, 0);
+            update_positions(1, true, false, r);
         }
 
         int drs_until = 0;
@@ -342,11 +381,16 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             // (tried: fetching the next lap's windows into registers at the end of the lap, under update_positions --
             //  6 more registers and 8 % slower: the other warps already cover the one round trip per lap)
             // pc / zc: draws of the window consumed so far.  A read past the end of the tape sets err (MCGP_ETAPE).
+            // Only the first window of U_py is staged up front (events + retirement tests + a typical lap's overtake draws
+            // fit: 24 + a few); an overtake pass stages further windows when its draws reach past what is there.
+            constexpr int kPyFirst = NP == 10 ? 32 : 64;
+            auto stage_py = [&](int from) {
+                const long long q = py.i + from + lane;
+                S_py[from + lane] = q < py.e ? py.p[q] : 0.5;
+            };
 #pragma unroll
-            for (int w = 0; w < kPyWin / 32; w++) {
-                const long long q = py.i + 32 * w + lane;
-                S_py[32 * w + lane] = q < py.e ? py.p[q] : 0.5;
-            }
+            for (int w = 0; w < kPyFirst / 32; w++) stage_py(32 * w);
+            int staged = kPyFirst;
             {
                 const long long q = zz.i + lane;
                 S_z[lane] = q < zz.e ? zz.p[q] : 0.5;
@@ -461,26 +505,34 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
 
             // ---- _simulate_overtakes :496-536 --------------------------------------------------
             bool have_r = false;  // r / S_inv / S_cum below describe the current times (the last pass changed nothing)
-            int r = 0;
             {
                 const double op = R.pace[drv] + (double)age * deg;  // :514-515 (raw driver deg)
                 const double op_pub = dnf ? __longlong_as_double(0x7ff8000000000000ll) : op;  // NaN: a retired car blocks its pairs (Q5)
-                bool guessed = false;  // r is the previous order with every run of successes reversed: verified below
+                // First ordering of the lap (:506), from a guess: a lap moves few cars far, so the new rank is the old one
+                // plus the crossings counted against the two old neighbours on each side (times by OLD rank through W);
+                // like the run-reversal guess of the later passes it is VERIFIED below and recounted on a miss.
+                if (is_car) W[r] = cum;
+                __syncwarp();
+                if (is_car) {
+                    const double a1 = W[r - 1], a2 = W[r - 2], b1 = W[r + 1], b2 = W[r + 2];
+                    r += (int)(b1 < cum) + (int)(b2 < cum) - (int)(cum < a1) - (int)(cum < a2);
+                }
                 for (int pass = 0; pass < 3; pass++) {
-                    if (!guessed) r = rank_set<NP>(cum, nmask, lane, S_p);  // ALL cars, retired ones included (Q5)
                     if (is_car) { S_inv[r] = lane; S_cum[r] = cum; S_op[r] = op_pub; }
+                    const uint32_t cover = __reduce_or_sync(RFULL, is_car ? (1u << r) : 0u);
                     __syncwarp();
-                    if (guessed) {
-                        // The re-written times descend by 0.1 s inside a run, so the new order is almost always the old one
-                        // with each run reversed; it is THE order iff (time, grid slot) increases strictly along it.
+                    {
+                        // r is a guess (window placement / every run of the last pass reversed: the re-written times descend
+                        // by 0.1 s inside a run); it is THE order iff it is a permutation along which (time, grid slot)
+                        // increases strictly.
                         bool ok = true;
                         if (is_car && r > 0) {
                             const double c_prev = S_cum[r - 1];
                             ok = c_prev < cum || (c_prev == cum && (int)S_inv[r - 1] < lane);
                         }
-                        if (!__all_sync(RFULL, ok)) {
+                        if (cover != nmask || !__all_sync(RFULL, ok)) {
                             __syncwarp();
-                            r = rank_set<NP>(cum, nmask, lane, S_p);
+                            r = rank_set<NP>(cum, nmask, lane, S_p);  // ALL cars, retired ones included (Q5)
                             if (is_car) { S_inv[r] = lane; S_cum[r] = cum; S_op[r] = op_pub; }
                             __syncwarp();
                         }
@@ -490,6 +542,11 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     if (drs) delta += R.drs_delta;
                     const bool cond = is_car && r > 0 && !dnf && delta > R.ovt_delta;
                     const uint32_t CM = __reduce_or_sync(RFULL, cond ? (1u << r) : 0u);
+                    while (pc + __popc(CM) > staged) {  // (warp-uniform; at most twice per lap)
+                        stage_py(staged);
+                        staged += 32;
+                        __syncwarp();
+                    }
                     const double u = py_draw(__popc(CM & ((1u << r) - 1u)), cond);  // draws in sorted order :524
                     pc += __popc(CM);
                     double prob = delta / 2.0;
@@ -510,7 +567,6 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     if (steps > 0) cum = sn ? a + 0.3 : a;
                     // presumed order for the next pass: every run [j, e] reversed
                     if (is_car) r = j + __ffs(~((M >> r) >> 1)) - 1;   // j + e - r with e = r + (successes right behind this car)
-                    guessed = true;
                     __syncwarp();
                 }
             }
@@ -562,7 +618,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
 cudaError_t launch_replay(const ReplayRace* race_dev, int n_drivers, unsigned long long n_sims, const double* u_py, const double* z,
                           const double* u_np, const long long* off, unsigned long long* hist, uint8_t* finish,
                           double* times, int16_t* dnf_lap, uint8_t* grid, long long* used, int* status,
-                          unsigned long long* work_counter, int sm_count, cudaStream_t st) {
+                          unsigned long long* work_counter, int sm_count, cudaStream_t st, bool serial_grid) {
     auto kern = n_drivers <= 20 ? replay_race_kernel<10> : replay_race_kernel<16>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRThreads, 0);
@@ -574,7 +630,7 @@ cudaError_t launch_replay(const ReplayRace* race_dev, int n_drivers, unsigned lo
     if (blocks < 1) blocks = 1;
     init_work_counters<<<1, 32, 0, st>>>(work_counter, 1, (unsigned long long)blocks * kRWarps);
     kern<<<(unsigned)blocks, kRThreads, 0, st>>>(race_dev, n_sims, u_py, z, u_np, off, hist, finish, times,
-                                                 dnf_lap, grid, used, status, work_counter);
+                                                 dnf_lap, grid, used, status, work_counter, serial_grid ? 1 : 0);
     return cudaGetLastError();
 }
 

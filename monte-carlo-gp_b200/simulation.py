@@ -247,11 +247,18 @@ class RaceSimulator:
 
     # -- replay mode (verification): consume the reference's own draws, bit-exact -----------------------
     def replay(self, grid_probs, base_pace, tire_deg, driver_variance, driver_dnf_rates=None, track_condition='dry',
-               *, u_py, z, u_np, offsets) -> dict:
+               *, u_py, z, u_np, offsets, serial_grid: bool = False) -> dict:
         """FP64 replay of explicit draw tapes (see include/mcgp.h mcgp_run_replay).  Returns per-sim arrays
-        (finish, times, dnf_lap, grid, used) and the count table."""
+        (finish, times, dnf_lap, grid, used) and the count table.  serial_grid=True evaluates every _sample_grid
+        position in the reference's serial operation order (include/mcgp.h: mcgp_replay_serial_grid); the default
+        does so only where the kernel's parallel evaluation cannot certify the same selection -- same results."""
         params = self._params(grid_probs, base_pace, tire_deg, driver_variance, driver_dnf_rates, track_condition)
-        return self._engine().run_replay(params, u_py, z, u_np, offsets)
+        eng = self._engine()
+        eng.replay_serial_grid(serial_grid)
+        try:
+            return eng.run_replay(params, u_py, z, u_np, offsets)
+        finally:
+            eng.replay_serial_grid(False)
 
 
 def run_batch(simulators_and_inputs: list[tuple[RaceSimulator, dict]], n_simulations: int, seed: int | None = None,

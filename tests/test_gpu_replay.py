@@ -22,13 +22,13 @@ def mcgp():
     return mcgp_b200
 
 
-def _replay(mcgp, oracle, cfg, mc, seed, n_sims, pop_a, pop_b):
+def _replay(mcgp, oracle, cfg, mc, seed, n_sims, pop_a, pop_b, serial_grid=False):
     oparams = oracle.make_params(cfg, mc, pop_a, pop_b)
     ref = oracle.run_streams(oparams, oracle.Rng(seed), n_sims, detail=True, tapes=True)
     sim = mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**cfg), pop_no_medium=pop_a, pop_no_soft=pop_b)
     kw = {k: mc.get(k) for k in ("grid_probs", "base_pace", "tire_deg", "driver_variance", "driver_dnf_rates")}
     got = sim.replay(**kw, track_condition=mc.get("track_condition", "dry"), u_py=ref["tape_upy"], z=ref["tape_z"],
-                     u_np=ref["tape_unp"], offsets=ref["tape_off"])
+                     u_np=ref["tape_unp"], offsets=ref["tape_off"], serial_grid=serial_grid)
     return ref, got
 
 
@@ -52,6 +52,61 @@ def test_replay_matches_reference_fixture(mcgp, oracle, name):
     assert np.array_equal(got["hist"].astype(np.int64), ref["hist"])
     if n_sims == meta["n_sims"]:
         assert np.array_equal(got["hist"].astype(np.int64), g["hist"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_replay_serial_grid_path_gives_the_same_races(mcgp, oracle, name):
+    """_sample_grid: the kernel's certified parallel selection and the serial evaluation in the reference's operation
+    order (which it falls back to where it cannot certify) are both bit-exact to the reference on every fixture."""
+    g = load_golden(name)
+    meta = g["meta"]
+    cfg, mc, seed, _ = gc.get_case(_case_of(name))
+    n_sims = min(meta["n_sims"], 1000)
+    ref, got = _replay(mcgp, oracle, cfg, mc, seed, n_sims, meta["pop_no_medium"], meta["pop_no_soft"], serial_grid=True)
+    k = min(g["finish"].shape[0], n_sims)
+    assert np.array_equal(got["grid"][:k], g["grid"][:k]), "serial-path grids differ from the reference"
+    assert np.array_equal(got["finish"], ref["finish"])
+    assert np.array_equal(got["times"].view(np.uint64), ref["times"].view(np.uint64))
+    assert np.array_equal(got["used"].cumsum(0), ref["draws"])
+
+
+def _boundary_tapes(mc, laps, n_sims, seed=7):
+    """Worst-case-sized synthetic tapes whose FIRST grid draw of every sim sits on (or one ulp either side of) a
+    boundary of the reference's cdf = cumsum(p / sum(p)) / cumsum(...)[-1] of grid position 0."""
+    drivers = list(mc["grid_probs"])
+    n = len(drivers)
+    n_py, n_z = n + (laps - 1) * (4 + n + 3 * (n - 1)), 2 * n + (laps - 1) * n
+    rng = np.random.default_rng(seed)
+    upy, z, unp = rng.random(n_sims * n_py), rng.standard_normal(n_sims * n_z), rng.random(n_sims * n)
+    off = np.arange(n_sims + 1, dtype=np.int64)[:, None] * np.array([n_py, n_z, n], np.int64)
+    p = [float(mc["grid_probs"][d][0]) for d in drivers]
+    tot = sum(p)                                  # builtin sum() as upstream (:123)
+    cdf = np.array([x / tot for x in p]).cumsum()
+    cdf = cdf / cdf[-1]
+    inner = np.flatnonzero(np.diff(np.concatenate([[0.0], cdf])) > 0)[:-1]
+    first = np.zeros(n_sims, np.int64)            # searchsorted(cdf, u, side='right') of the edited draw
+    for s in range(n_sims):
+        b = cdf[rng.choice(inner)]
+        unp[off[s, 2]] = [np.nextafter(b, 0.0), b, np.nextafter(b, 1.0)][s % 3]
+        first[s] = int((cdf <= unp[off[s, 2]]).sum())
+    return upy, z, unp, off, first
+
+
+def test_replay_grid_draw_on_a_boundary_takes_the_serial_path(mcgp, oracle):
+    """Uniforms placed ON (and one ulp either side of) the cumulative-probability boundaries of a grid row: the
+    parallel selection cannot certify these; the serial path decides them exactly as the oracle does."""
+    cfg, mc, _, _ = gc.get_case("bahrain_dry")
+    oparams = oracle.make_params(cfg, mc, "SOFT", "MEDIUM")
+    upy, z, unp, off, first = _boundary_tapes(mc, cfg["total_laps"], 900)
+    want = oracle.run_tapes(oparams, upy, z, unp, off, detail=True)
+    assert np.array_equal(want["grid"][:, 0], first)   # the draw one ulp below a boundary selects the driver before it
+    sim = mcgp.simulation.RaceSimulator(mcgp.simulation.RaceConfig(**cfg), pop_no_medium="SOFT", pop_no_soft="MEDIUM")
+    kw = {k: mc.get(k) for k in ("grid_probs", "base_pace", "tire_deg", "driver_variance", "driver_dnf_rates")}
+    for serial in (False, True):
+        got = sim.replay(**kw, u_py=upy, z=z, u_np=unp, offsets=off, serial_grid=serial)
+        assert np.array_equal(got["grid"], want["grid"]), f"grids differ from the oracle (serial_grid={serial})"
+        assert np.array_equal(got["finish"], want["finish"])
+        assert np.array_equal(got["times"].view(np.uint64), want["times"].view(np.uint64))
 
 
 def test_replay_tape_overrun_is_an_error(mcgp, oracle):
