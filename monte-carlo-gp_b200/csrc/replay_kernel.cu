@@ -9,6 +9,7 @@
 // (grid order) a lane-ordered prefix count (ballot + popc) over the tape cursors, and makes
 // the reference's stable-sort tie-break (list order) a plain (time, lane) comparison.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "device_params.h"
@@ -184,6 +185,12 @@ __device__ __noinline__ int sample_slot_serial(double* S_p, double* S_c, double 
     return sel;
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS: no register, no scoreboard wait at the issue site)
+__device__ __forceinline__ void cp_async8(uint32_t dst_sh, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_sh), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 #ifndef MCGP_REPLAY_MIN_BLOCKS
 #define MCGP_REPLAY_MIN_BLOCKS 6   // resident 128-thread blocks per SM the register budget is tuned for (80 registers: 17.8 M races/s; 5 blocks / 96 registers: 16.5 M)
 #endif
@@ -196,6 +203,10 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                    int* __restrict__ status, unsigned long long* __restrict__ work_counter, const int serial_grid) {
     // draws one lap can consume at most: 4 event draws + n retirement tests + 3 passes x (n - 1) pairs (U_py), n normals (Z)
     constexpr int kPyWin = NP == 10 ? 96 : 160, kZWin = 32;
+    // The two lap-loop tapes reach the kernel through per-warp RINGS in shared memory, filled with cp.async a lap or more
+    // ahead of their use: ring slot = (draw index within the sim) & (size - 1).  kPyAhead / kZAhead: how far beyond the
+    // cursor the fill is kept (one 32-draw group per lap tops it up).
+    constexpr int kPyRing = NP == 10 ? 128 : 256, kPyAhead = kPyRing - 32, kZRing = 128, kZAhead = 64;
     __shared__ ReplayRace R;
     __shared__ uint32_t hist_s[MCGP_LANES * MCGP_LANES];
     // Everything a warp exchanges through shared memory sits in ONE struct per warp, addressed from one pinned base
@@ -208,12 +219,13 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         // lap; the time at a run's start): one LDS each instead of a rank -> lane lookup plus two shuffles per double
         double cum[32], op[32], last[32];
         double win[36];            // first ordering of a lap: the new times by OLD rank between -inf / +inf pads (win[2 + rank])
-        // Per-warp windows of the two lap-loop tapes, refilled once per lap with coalesced loads.  The draw sites of a lap
-        // (events, retirement tests, noise, <= 3 overtake passes) depend on each other's outcome, so reading the tapes
-        // from global memory where they are consumed cost 5-6 dependent DRAM/L2 round trips per lap (ncu r2b: 2.3 stall
-        // cycles per issue on the long scoreboard, 14 % of all samples on the tape load); now it is one.
-        double py[kPyWin + 32];    // (+32: lanes that take no draw still index up to 31 past the cursor)
-        double z[kZWin];
+        // Per-warp rings of the two lap-loop tapes.  The draw sites of a lap (events, retirement tests, noise, <= 3
+        // overtake passes) depend on each other's outcome, so reading the tapes from global memory where they are consumed
+        // cost 5-6 dependent DRAM/L2 round trips per lap (ncu r2b: 2.3 stall cycles per issue on the long scoreboard);
+        // one coalesced refill per lap still exposed one (r2n: 2.4 per issue once the rest of the lap got shorter).  Now
+        // cp.async fills the rings a lap or more ahead and the lap reads shared memory only.
+        double py[kPyRing];
+        double z[kZRing];
         uint32_t inv[32];          // rank -> lane of the current all-cars order
     };
     __shared__ __align__(16) WarpScratch scratch[kRWarps];
@@ -225,8 +237,11 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch* ws = &scratch[warp];
-    asm volatile("" : "+l"(ws));   // one live base pointer; every array below is a constant offset from it
+    // one live base register (the 32-bit shared-window address, pinned); every array below is a constant offset from it,
+    // and converting it back with cvta keeps the accesses LDS / STS (a pinned generic pointer made them generic LD / ST)
+    uint32_t ws_sh = (uint32_t)__cvta_generic_to_shared(&scratch[warp]);
+    asm volatile("" : "+r"(ws_sh));
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(__cvta_shared_to_generic(ws_sh));
     double* const S_p = ws->p;
     double* const S_c = ws->c;
     uint32_t* const S_inv = ws->inv;
@@ -254,6 +269,34 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         Tape zz{zt, off[3 * s + 1], off[3 * s + 4]};
         Tape np{u_np, off[3 * s + 2], off[3 * s + 5]};
         const long long py0 = py.i, z0 = zz.i, np0 = np.i;
+        // Ring fill.  *_st: draws of this sim (counted from its first) staged or in flight; *_ok: of those, landed and
+        // visible to the whole warp.  A group = 32 consecutive draws, one per lane; a read past the end of the tape is
+        // clamped to its last draw (the overrun itself is detected where the draws are consumed).
+        int py_st = 0, py_ok = 0, z_st = 0, z_ok = 0;
+        auto fill_py = [&]() {
+            long long q = py0 + py_st + lane;
+            q = q < py.e ? q : py.e - 1;
+            if (q >= 0) cp_async8(ws_sh + (uint32_t)offsetof(WarpScratch, py) + 8u * (uint32_t)((py_st + lane) & (kPyRing - 1)), py.p + q);
+            py_st += 32;
+        };
+        auto fill_z = [&]() {
+            long long q = z0 + z_st + lane;
+            q = q < zz.e ? q : zz.e - 1;
+            if (q >= 0) cp_async8(ws_sh + (uint32_t)offsetof(WarpScratch, z) + 8u * (uint32_t)((z_st + lane) & (kZRing - 1)), zz.p + q);
+            z_st += 32;
+        };
+        auto landed = [&]() {  // everything issued so far has arrived and is visible to every lane
+            cp_async_wait_all();
+            __syncwarp();
+            py_ok = py_st;
+            z_ok = z_st;
+        };
+        cp_async_wait_all();  // (prefetches of the previous sim still in flight must not land on top of this sim's)
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < kPyAhead / 32; g++) fill_py();
+#pragma unroll
+        for (int g = 0; g < (kZAhead + 32) / 32; g++) fill_z();   // lap 1 takes up to 2 n normals
 
         // ---- _sample_grid (src/simulation.py:102-145) + RandomState.choice restated -------------
         int drv = 0;
@@ -355,12 +398,15 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         int r = 0;
         // ---- _simulate_lap_1 (:275-311) --------------------------------------------------------
         {
-            const double u = py.at(lane, is_car, err);
+            landed();  // (issued before the grid was sampled)
+            const double u = S_py[lane & (kPyRing - 1)];
+            if (is_car && py.i + lane >= py.e) err = 1;
             py.i += n;
             if (is_car && u < lap1_rate) { dnf = true; dnf_lap = 1; }
             const uint32_t surv = __ballot_sync(RFULL, !dnf);
             const int k = 2 * __popc(surv & lt_mask);
-            const double z_noise = zz.at(k, !dnf, err), z_start = zz.at(k + 1, !dnf, err);
+            const double z_noise = S_z[k & (kZRing - 1)], z_start = S_z[(k + 1) & (kZRing - 1)];
+            if (!dnf && zz.i + k + 1 >= zz.e) err = 1;
             zz.i += 2 * __popc(surv);
             if (!dnf) {
                 const double base_lap = lap_time(1, z_noise);
@@ -377,32 +423,21 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
 
         int drs_until = 0;
         for (int lap = 2; lap <= L; lap++) {
-            // ---- this lap's windows of the tapes: one coalesced refill, then shared-memory reads ----
-            // (tried: fetching the next lap's windows into registers at the end of the lap, under update_positions --
-            //  6 more registers and 8 % slower: the other warps already cover the one round trip per lap)
-            // pc / zc: draws of the window consumed so far.  A read past the end of the tape sets err (MCGP_ETAPE).
-            // Only the first window of U_py is staged up front (events + retirement tests + a typical lap's overtake draws
-            // fit: 24 + a few); an overtake pass stages further windows when its draws reach past what is there.
-            constexpr int kPyFirst = NP == 10 ? 32 : 64;
-            auto stage_py = [&](int from) {
-                const long long q = py.i + from + lane;
-                S_py[from + lane] = q < py.e ? py.p[q] : 0.5;
-            };
-#pragma unroll
-            for (int w = 0; w < kPyFirst / 32; w++) stage_py(32 * w);
-            int staged = kPyFirst;
-            {
-                const long long q = zz.i + lane;
-                S_z[lane] = q < zz.e ? zz.p[q] : 0.5;
-            }
-            __syncwarp();
+            // ---- this lap's draws: already in the rings ---------------------------------------------
+            // pc / zc: draws consumed so far this lap.  A read past the end of the tape sets err (MCGP_ETAPE).
+            // What was issued during the previous lap has had a lap to arrive; then top the rings up (typically one
+            // group each) -- those land under this lap's work and are not waited for before the next lap.
+            landed();
+            const int py_rel = (int)(py.i - py0), z_rel = (int)(zz.i - z0);
+            while (py_st - py_rel < kPyAhead) fill_py();
+            while (z_st - z_rel < kZAhead) fill_z();
+            if (py_ok - py_rel < 4 + n) landed();  // (only after a lap that consumed nearly a whole ring)
             int pc = 0, zc = 0;
             const long long py_left64 = py.e - py.i, z_left64 = zz.e - zz.i;
             const int py_left = py_left64 > kPyWin ? kPyWin : (int)py_left64;  // draws left on the tape (all that matters: < window)
             const int z_left = z_left64 > kZWin ? kZWin : (int)z_left64;
-            // the k-th unread U_py draw: a plain window read (k <= 31, so the index stays inside the window; entries past
-            // the end of the tape hold 0.5).  Whether the lap consumed more than the tape had left is checked once, below.
-            auto py_draw = [&](int k, bool) -> double { return S_py[pc + k]; };
+            // the k-th unread U_py draw: a ring read.  Whether the lap consumed more than the tape had left is checked once, below.
+            auto py_draw = [&](int k, bool) -> double { return S_py[(py_rel + pc + k) & (kPyRing - 1)]; };
 
             // ---- events :168-176 (short-circuit draws) ------------------------------------------
             int ev = 0;
@@ -468,7 +503,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 if (was_live && u < dnf_rate) { dnf = true; dnf_lap = lap; }
                 const uint32_t surv = __ballot_sync(RFULL, !dnf);
                 const int zk = __popc(surv & lt_mask);
-                const double z = S_z[zk];
+                const double z = S_z[(z_rel + zk) & (kZRing - 1)];
                 zc = __popc(surv);
                 if (!dnf) {
                     const double clean = lap_time(lap, z);
@@ -542,11 +577,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     if (drs) delta += R.drs_delta;
                     const bool cond = is_car && r > 0 && !dnf && delta > R.ovt_delta;
                     const uint32_t CM = __reduce_or_sync(RFULL, cond ? (1u << r) : 0u);
-                    while (pc + __popc(CM) > staged) {  // (warp-uniform; at most twice per lap)
-                        stage_py(staged);
-                        staged += 32;
-                        __syncwarp();
-                    }
+                    if (py_rel + pc + __popc(CM) > py_ok) landed();  // (warp-uniform, rare: the lap outran what had landed at its start)
                     const double u = py_draw(__popc(CM & ((1u << r) - 1u)), cond);  // draws in sorted order :524
                     pc += __popc(CM);
                     double prob = delta / 2.0;
