@@ -64,7 +64,7 @@ __device__ __forceinline__ int rank_set(double v, uint32_t in_set, int lane, dou
         for (int j = 0; j < lane; j++) cnt += (S_key[j] == v) ? 1 : 0;
     }
     __syncwarp();
-    return cnt;
+    return member ? cnt : lane;  // (lanes outside the set keep their own index: the all-cars order stays a permutation of 0..31)
 }
 
 // CPython 3.12 builtin sum() over items P[0..n) with kinds K[0..n)  (executed uniformly by all lanes)
@@ -217,7 +217,8 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         double c[32];              // running cumsum of the grid probabilities (first bytes: item kinds on the general sum() path)
         // rank-indexed copies of what a car needs from its neighbours in the order (the car ahead's pace, time and last
         // lap; the time at a run's start): one LDS each instead of a rank -> lane lookup plus two shuffles per double
-        double cum[32], op[32], last[32];
+        // ([-1] pads: "the car ahead of the leader" has time -inf and no pace, so rank 0 needs no special case)
+        double cum_pad, cum[32], op_pad, op[32], last[32];
         double win[36];            // first ordering of a lap: the new times by OLD rank between -inf / +inf pads (win[2 + rank])
         // Per-warp rings of the two lap-loop tapes.  The draw sites of a lap (events, retirement tests, noise, <= 3
         // overtake passes) depend on each other's outcome, so reading the tapes from global memory where they are consumed
@@ -252,6 +253,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     double* const S_z = ws->z;
     double* const W = ws->win + 2;
     for (int i = lane; i < 36; i += 32) ws->win[i] = __longlong_as_double(i < 2 ? 0xfff0000000000000ll : 0x7ff0000000000000ll);
+    if (lane == 0) { ws->cum_pad = __longlong_as_double(0xfff0000000000000ll); ws->op_pad = __longlong_as_double(0x7ff8000000000000ll); }
     __syncwarp();
     const int n = R.n, L = R.total_laps, track = R.track;
     const bool is_car = lane < n;
@@ -352,7 +354,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         bool dnf = !is_car, drs = false;
         int dnf_lap = 0, pos_live = 0;
         double t_lead = 0.0;  // time of the leading runner as of the last update_positions (warp-uniform)
-        double cum = 0.0, last = 0.0, tbl = 0.0, ahead_last = 0.0;
+        // Lanes without a car behave like cars parked behind the field for good: time +inf, retired from the start, rank ==
+        // lane.  The rank-indexed exchanges below then need no `is_car` guard.
+        double cum = is_car ? 0.0 : __longlong_as_double(0x7ff0000000000000ll), last = 0.0, tbl = 0.0, ahead_last = 0.0;
 
         // _calculate_lap_time :313-332, strictly left to right
         auto lap_time = [&](int lap, double z) -> double {
@@ -371,11 +375,12 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         auto update_positions = [&](int lap, bool drs_disabled, bool have_r, int& r_all) {
             if (!have_r) {
                 r_all = rank_set<NP>(cum, nmask, lane, S_p);
-                if (is_car) { S_inv[r_all] = lane; S_cum[r_all] = cum; }
+                S_inv[r_all] = lane;
+                S_cum[r_all] = cum;
             }
-            if (is_car) S_last[r_all] = last;
+            S_last[r_all] = last;
             __syncwarp();
-            const bool runner = is_car && !dnf;
+            const bool runner = !dnf;
             const uint32_t LM = __reduce_or_sync(RFULL, runner ? (1u << r_all) : 0u);  // ranks held by runners
             if (LM) {
                 t_lead = S_cum[__ffs(LM) - 1];
@@ -395,7 +400,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
 
         // r: this car's rank among ALL cars by (time, grid slot) as of the last update_positions -- the guess the next
         // lap's first ordering starts from
-        int r = 0;
+        int r = lane;
         // ---- _simulate_lap_1 (:275-311) --------------------------------------------------------
         {
             landed();  // (issued before the grid was sampled)
@@ -546,36 +551,37 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 // First ordering of the lap (:506), from a guess: a lap moves few cars far, so the new rank is the old one
                 // plus the crossings counted against the two old neighbours on each side (times by OLD rank through W);
                 // like the run-reversal guess of the later passes it is VERIFIED below and recounted on a miss.
-                if (is_car) W[r] = cum;
+                W[r] = cum;
                 __syncwarp();
-                if (is_car) {
+                {
                     const double a1 = W[r - 1], a2 = W[r - 2], b1 = W[r + 1], b2 = W[r + 2];
                     r += (int)(b1 < cum) + (int)(b2 < cum) - (int)(cum < a1) - (int)(cum < a2);
                 }
                 for (int pass = 0; pass < 3; pass++) {
-                    if (is_car) { S_inv[r] = lane; S_cum[r] = cum; S_op[r] = op_pub; }
-                    const uint32_t cover = __reduce_or_sync(RFULL, is_car ? (1u << r) : 0u);
+                    S_inv[r] = lane;
+                    S_cum[r] = cum;
+                    S_op[r] = op_pub;
+                    const uint32_t cover = __reduce_or_sync(RFULL, 1u << r);
                     __syncwarp();
                     {
                         // r is a guess (window placement / every run of the last pass reversed: the re-written times descend
                         // by 0.1 s inside a run); it is THE order iff it is a permutation along which (time, grid slot)
                         // increases strictly.
-                        bool ok = true;
-                        if (is_car && r > 0) {
-                            const double c_prev = S_cum[r - 1];
-                            ok = c_prev < cum || (c_prev == cum && (int)S_inv[r - 1] < lane);
-                        }
-                        if (cover != nmask || !__all_sync(RFULL, ok)) {
+                        const double c_prev = S_cum[r - 1];  // (rank 0 reads the -inf pad)
+                        const bool ok = c_prev < cum || (c_prev == cum && (int)S_inv[(r - 1) & 31] < lane);
+                        if (cover != RFULL || !__all_sync(RFULL, ok)) {
                             __syncwarp();
                             r = rank_set<NP>(cum, nmask, lane, S_p);  // ALL cars, retired ones included (Q5)
-                            if (is_car) { S_inv[r] = lane; S_cum[r] = cum; S_op[r] = op_pub; }
+                            S_inv[r] = lane;
+                            S_cum[r] = cum;
+                            S_op[r] = op_pub;
                             __syncwarp();
                         }
                     }
-                    const double op_a = S_op[(r > 0 ? r - 1 : 0) & 31];
-                    double delta = op_a - op;   // NaN if the car ahead is retired: every comparison below is false
+                    const double op_a = S_op[r - 1];  // (rank 0 reads the NaN pad)
+                    double delta = op_a - op;   // NaN if the car ahead is retired (or there is none): every comparison below is false
                     if (drs) delta += R.drs_delta;
-                    const bool cond = is_car && r > 0 && !dnf && delta > R.ovt_delta;
+                    const bool cond = !dnf && delta > R.ovt_delta;
                     const uint32_t CM = __reduce_or_sync(RFULL, cond ? (1u << r) : 0u);
                     if (py_rel + pc + __popc(CM) > py_ok) landed();  // (warp-uniform, rare: the lap outran what had landed at its start)
                     const double u = py_draw(__popc(CM & ((1u << r) - 1u)), cond);  // draws in sorted order :524
@@ -588,16 +594,16 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     // sequential re-write chain :528-530, replayed op by op for bit-exactness
                     const uint32_t clear_below = ~M & ((2u << r) - 1u);
                     const int j = 31 - __clz(clear_below);
-                    const int k = is_car ? r - j : 0;
+                    const int k = r - j;   // (lanes without a car: no bit of M at or above their rank, so j == r and sn == 0)
                     double a = S_cum[j & 31];
-                    const int sn = is_car ? (int)(((M >> r) >> 1) & 1u) : 0;
+                    const int sn = (int)(((M >> r) >> 1) & 1u);
                     const int steps = k + sn;
                     const int max_steps = __reduce_max_sync(RFULL, steps);
                     for (int q = 0; q < max_steps; q++)
                         if (q < steps) { a = a - 0.1; if (!(a > 0.1)) a = 0.1; }  // max(0.1, ahead - 0.1)
                     if (steps > 0) cum = sn ? a + 0.3 : a;
                     // presumed order for the next pass: every run [j, e] reversed
-                    if (is_car) r = j + __ffs(~((M >> r) >> 1)) - 1;   // j + e - r with e = r + (successes right behind this car)
+                    r = j + __ffs(~((M >> r) >> 1)) - 1;   // j + e - r with e = r + (successes right behind this car)
                     __syncwarp();
                 }
             }
