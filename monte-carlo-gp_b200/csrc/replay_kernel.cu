@@ -202,7 +202,6 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                    int16_t* __restrict__ dnf_lap_out, uint8_t* __restrict__ grid_out, long long* __restrict__ used_out,
                    int* __restrict__ status, unsigned long long* __restrict__ work_counter, const int serial_grid) {
     // draws one lap can consume at most: 4 event draws + n retirement tests + 3 passes x (n - 1) pairs (U_py), n normals (Z)
-    constexpr int kPyWin = NP == 10 ? 96 : 160, kZWin = 32;
     // The two lap-loop tapes reach the kernel through per-warp RINGS in shared memory, filled with cp.async a lap or more
     // ahead of their use: ring slot = (draw index within the sim) & (size - 1).  kPyAhead / kZAhead: how far beyond the
     // cursor the fill is kept (one 32-draw group per lap tops it up).
@@ -267,24 +266,30 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     for (unsigned long long s = (unsigned long long)blockIdx.x * kRWarps + warp; s < n_sims;) {
         unsigned long long s_next = 0;
         if (lane == 0) s_next = atomicAdd(work_counter, 1ull);
-        Tape py{u_py, off[3 * s], off[3 * s + 3]};
-        Tape zz{zt, off[3 * s + 1], off[3 * s + 4]};
+        // U_py and Z: this sim's stretch of the tape as a base pointer + 32-bit cursors (py_rel / z_rel: draws consumed,
+        // py_len / z_len: draws the tape holds for this sim)
+        const long long py0 = off[3 * s], z0 = off[3 * s + 1];
+        const double* const py_base = u_py + py0;
+        const double* const z_base = zt + z0;
+        const long long py_len64 = off[3 * s + 3] - py0, z_len64 = off[3 * s + 4] - z0;
+        const int py_len = py_len64 > 0x40000000 ? 0x40000000 : (int)py_len64, z_len = z_len64 > 0x40000000 ? 0x40000000 : (int)z_len64;
+        int py_rel = 0, z_rel = 0;
         Tape np{u_np, off[3 * s + 2], off[3 * s + 5]};
-        const long long py0 = py.i, z0 = zz.i, np0 = np.i;
+        const long long np0 = np.i;
         // Ring fill.  *_st: draws of this sim (counted from its first) staged or in flight; *_ok: of those, landed and
         // visible to the whole warp.  A group = 32 consecutive draws, one per lane; a read past the end of the tape is
         // clamped to its last draw (the overrun itself is detected where the draws are consumed).
         int py_st = 0, py_ok = 0, z_st = 0, z_ok = 0;
         auto fill_py = [&]() {
-            long long q = py0 + py_st + lane;
-            q = q < py.e ? q : py.e - 1;
-            if (q >= 0) cp_async8(ws_sh + (uint32_t)offsetof(WarpScratch, py) + 8u * (uint32_t)((py_st + lane) & (kPyRing - 1)), py.p + q);
+            int q = py_st + lane;
+            q = q < py_len ? q : py_len - 1;
+            if (q >= 0) cp_async8(ws_sh + (uint32_t)offsetof(WarpScratch, py) + 8u * (uint32_t)((py_st + lane) & (kPyRing - 1)), py_base + q);
             py_st += 32;
         };
         auto fill_z = [&]() {
-            long long q = z0 + z_st + lane;
-            q = q < zz.e ? q : zz.e - 1;
-            if (q >= 0) cp_async8(ws_sh + (uint32_t)offsetof(WarpScratch, z) + 8u * (uint32_t)((z_st + lane) & (kZRing - 1)), zz.p + q);
+            int q = z_st + lane;
+            q = q < z_len ? q : z_len - 1;
+            if (q >= 0) cp_async8(ws_sh + (uint32_t)offsetof(WarpScratch, z) + 8u * (uint32_t)((z_st + lane) & (kZRing - 1)), z_base + q);
             z_st += 32;
         };
         auto landed = [&]() {  // everything issued so far has arrived and is visible to every lane
@@ -405,14 +410,14 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         {
             landed();  // (issued before the grid was sampled)
             const double u = S_py[lane & (kPyRing - 1)];
-            if (is_car && py.i + lane >= py.e) err = 1;
-            py.i += n;
+            if (is_car && lane >= py_len) err = 1;
+            py_rel = n;
             if (is_car && u < lap1_rate) { dnf = true; dnf_lap = 1; }
             const uint32_t surv = __ballot_sync(RFULL, !dnf);
             const int k = 2 * __popc(surv & lt_mask);
             const double z_noise = S_z[k & (kZRing - 1)], z_start = S_z[(k + 1) & (kZRing - 1)];
-            if (!dnf && zz.i + k + 1 >= zz.e) err = 1;
-            zz.i += 2 * __popc(surv);
+            if (!dnf && k + 1 >= z_len) err = 1;
+            z_rel = 2 * __popc(surv);
             if (!dnf) {
                 const double base_lap = lap_time(1, z_noise);
                 double pf = 0.5 + (double)(lane + 1) * 0.1;
@@ -433,14 +438,10 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
             // What was issued during the previous lap has had a lap to arrive; then top the rings up (typically one
             // group each) -- those land under this lap's work and are not waited for before the next lap.
             landed();
-            const int py_rel = (int)(py.i - py0), z_rel = (int)(zz.i - z0);
             while (py_st - py_rel < kPyAhead) fill_py();
             while (z_st - z_rel < kZAhead) fill_z();
             if (py_ok - py_rel < 4 + n) landed();  // (only after a lap that consumed nearly a whole ring)
             int pc = 0, zc = 0;
-            const long long py_left64 = py.e - py.i, z_left64 = zz.e - zz.i;
-            const int py_left = py_left64 > kPyWin ? kPyWin : (int)py_left64;  // draws left on the tape (all that matters: < window)
-            const int z_left = z_left64 > kZWin ? kZWin : (int)z_left64;
             // the k-th unread U_py draw: a ring read.  Whether the lap consumed more than the tape had left is checked once, below.
             auto py_draw = [&](int k, bool) -> double { return S_py[(py_rel + pc + k) & (kPyRing - 1)]; };
 
@@ -510,18 +511,15 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 const int zk = __popc(surv & lt_mask);
                 const double z = S_z[(z_rel + zk) & (kZRing - 1)];
                 zc = __popc(surv);
-                if (!dnf) {
+                {   // (evaluated by every lane, kept by the runners: no divergent region around ~25 FP64 instructions)
                     const double clean = lap_time(lap, z);
-                    double lt = clean;
-                    if (tbl > 0) {
-                        if (ahead_last > 0 && tbl < R.dirty_thr) {
-                            const double dirty = clean + R.dirty_pen;
-                            lt = dirty >= ahead_last ? dirty : ahead_last;
-                        }
-                    }
-                    cum += lt;
-                    last = lt;
-                    age += 1;
+                    const double dirty = clean + R.dirty_pen;
+                    const bool in_dirty_air = tbl > 0 && ahead_last > 0 && tbl < R.dirty_thr;
+                    const double lt = in_dirty_air ? (dirty >= ahead_last ? dirty : ahead_last) : clean;
+                    const double cum_new = cum + lt;
+                    cum = dnf ? cum : cum_new;
+                    last = dnf ? last : lt;
+                    age += dnf ? 0 : 1;
                 }
             }
 
@@ -607,9 +605,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     __syncwarp();
                 }
             }
-            if (pc > py_left || zc > z_left) err = 1;  // the lap read past the end of a tape (MCGP_ETAPE)
-            py.i += pc;
-            zz.i += zc;
+            py_rel += pc;
+            z_rel += zc;
+            if (py_rel > py_len || z_rel > z_len) err = 1;  // the lap read past the end of a tape (MCGP_ETAPE)
             update_positions(lap, lap <= drs_until, have_r, r);
         }
 
@@ -636,8 +634,8 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 if (grid_out) grid_out[o + lane] = (uint8_t)drv;
             }
             if (used_out && lane == 0) {
-                used_out[3 * s] = py.i - py0;
-                used_out[3 * s + 1] = zz.i - z0;
+                used_out[3 * s] = py_rel;
+                used_out[3 * s + 1] = z_rel;
                 used_out[3 * s + 2] = np.i - np0;
             }
         }
