@@ -192,7 +192,7 @@ __device__ __forceinline__ void cp_async8(uint32_t dst_sh, const double* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 #ifndef MCGP_REPLAY_MIN_BLOCKS
-#define MCGP_REPLAY_MIN_BLOCKS 6   // resident 128-thread blocks per SM the register budget is tuned for (80 registers: 17.8 M races/s; 5 blocks / 96 registers: 16.5 M)
+#define MCGP_REPLAY_MIN_BLOCKS 7   // resident 128-thread blocks per SM the register budget is tuned for (r2p A/B: 5 blocks / 96 registers 27.6 M, 6 / 80 29.7 M, 7 / 72 30.7 M races/s)
 #endif
 template <int NP>
 __global__ void __launch_bounds__(kRThreads, MCGP_REPLAY_MIN_BLOCKS)
