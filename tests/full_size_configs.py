@@ -39,8 +39,11 @@ def main() -> None:
     ap.add_argument("--out", default="")
     ap.add_argument("--scale", type=float, default=1.0, help="multiply every sim count (smoke runs: 0.001)")
     ap.add_argument("--ref-sims", type=int, default=400_000)
-    args = ap.parse_args()
+    run(ap.parse_args())
 
+
+def run(args) -> dict:
+    """The whole pass; `args` carries .scale, .ref_sims and .out.  Returns the result dict (every rank)."""
     import torch
     import torch.distributed as dist
     import mcgp_b200 as mcgp
@@ -187,6 +190,7 @@ def main() -> None:
                 f.write(line + "\n")
     if world > 1:
         dist.destroy_process_group()
+    return res
 
 
 if __name__ == "__main__":
