@@ -109,6 +109,30 @@ def test_replay_grid_draw_on_a_boundary_takes_the_serial_path(mcgp, oracle):
         assert np.array_equal(got["times"].view(np.uint64), want["times"].view(np.uint64))
 
 
+@pytest.mark.parametrize("block", range(4))
+def test_replay_random_configurations(mcgp, oracle, block):
+    """Randomised sweep of the parameter space (1-32 cars: both kernel instantiations; 1-90 laps; event storms; certain /
+    impossible retirements; zero variance: exact ties; one-hot, flat and sparse grids with all-zero rows: the serial
+    grid path; all track conditions; both pop knobs): every race bit-exact against the oracle, with the certified scan
+    and with the serial grid path forced."""
+    import random
+    from test_gpu_native import _random_case
+    rnd = random.Random(4200 + block)
+    for trial in range(6):
+        cfg, mc = _random_case(rnd)
+        pop = (rnd.choice(["SOFT", "HARD"]), rnd.choice(["MEDIUM", "HARD"]))
+        n_sims = 400
+        what = f"block {block} trial {trial}: n={len(mc['grid_probs'])} laps={cfg['total_laps']} {mc['track_condition']}"
+        for serial in (False, True):
+            ref, got = _replay(mcgp, oracle, cfg, mc, rnd.getrandbits(32) if not serial else 99, n_sims, *pop, serial_grid=serial)
+            assert np.array_equal(got["grid"], ref["grid"]), what
+            bad = np.nonzero((got["finish"] != ref["finish"]).any(1))[0]
+            assert bad.size == 0, f"{what}: {bad.size} of {n_sims} races differ from the oracle, first: sim {bad[:5]}"
+            assert np.array_equal(got["times"].view(np.uint64), ref["times"].view(np.uint64)), what
+            assert np.array_equal(got["dnf_lap"], ref["dnf_lap"]), what
+            assert np.array_equal(got["used"].cumsum(0), ref["draws"]), what
+
+
 def test_replay_tape_overrun_is_an_error(mcgp, oracle):
     cfg, mc, seed, _ = gc.get_case("small_grids")
     oparams = oracle.make_params(cfg, mc)
