@@ -236,7 +236,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         for (int i = threadIdx.x; i < MCGP_LANES * MCGP_LANES; i += kRThreads) hist_s[i] = 0;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(RFULL, (int)(threadIdx.x >> 5), 0);
     // one live base register (the 32-bit shared-window address, pinned); every array below is a constant offset from it,
     // and converting it back with cvta keeps the accesses LDS / STS (a pinned generic pointer made them generic LD / ST)
     uint32_t ws_sh = (uint32_t)__cvta_generic_to_shared(&scratch[warp]);
@@ -254,7 +254,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     for (int i = lane; i < 36; i += 32) ws->win[i] = __longlong_as_double(i < 2 ? 0xfff0000000000000ll : 0x7ff0000000000000ll);
     if (lane == 0) { ws->cum_pad = __longlong_as_double(0xfff0000000000000ll); ws->op_pad = __longlong_as_double(0x7ff8000000000000ll); }
     __syncwarp();
-    const int n = R.n, L = R.total_laps, track = R.track;
+    // warp-uniform values are broadcast from lane 0 so that the compiler can PROVE them uniform: loops and branches on them
+    // are then convergent and need no divergence guards (BSSY / BSYNC around every block, BRA.DIV around every __syncwarp)
+    const int n = __shfl_sync(RFULL, R.n, 0), L = __shfl_sync(RFULL, R.total_laps, 0), track = __shfl_sync(RFULL, R.track, 0);
     const bool is_car = lane < n;
     const uint32_t nmask = n >= 32 ? RFULL : ((1u << n) - 1u);
     uint32_t lt_mask = (1u << lane) - 1u;
@@ -459,6 +461,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     }
                 }
             }
+            ev = __shfl_sync(RFULL, ev, 0);  // (every lane read the same draws: make the uniformity provable)
             if (ev) {
                 const uint32_t live_m = __ballot_sync(RFULL, !dnf);
                 if (live_m) {
