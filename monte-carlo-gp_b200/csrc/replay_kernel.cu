@@ -218,7 +218,10 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         // lap; the time at a run's start): one LDS each instead of a rank -> lane lookup plus two shuffles per double
         // ([-1] pads: "the car ahead of the leader" has time -inf and no pace, so rank 0 needs no special case)
         double cum_pad, cum[32], op_pad, op[32], last[32];
-        double win[36];            // first ordering of a lap: the new times by OLD rank between -inf / +inf pads (win[2 + rank])
+        // first ordering of a lap: the new times by OLD rank between -inf / +inf pads (win[2 + rank]) -- as FLOATS relative to
+        // the previous leader: they only feed a guess that is verified in FP64, and a 4-byte rank-permuted exchange is one
+        // conflict-free wavefront where an 8-byte one is two to four (ncu r2s: the LSU data pipe at 81 %, busier than the issue port)
+        float win[36];
         // Per-warp rings of the two lap-loop tapes.  The draw sites of a lap (events, retirement tests, noise, <= 3
         // overtake passes) depend on each other's outcome, so reading the tapes from global memory where they are consumed
         // cost 5-6 dependent DRAM/L2 round trips per lap (ncu r2b: 2.3 stall cycles per issue on the long scoreboard);
@@ -250,8 +253,8 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
     double* const S_last = ws->last;
     double* const S_py = ws->py;
     double* const S_z = ws->z;
-    double* const W = ws->win + 2;
-    for (int i = lane; i < 36; i += 32) ws->win[i] = __longlong_as_double(i < 2 ? 0xfff0000000000000ll : 0x7ff0000000000000ll);
+    float* const W = ws->win + 2;
+    for (int i = lane; i < 36; i += 32) ws->win[i] = __int_as_float(i < 2 ? 0xff800000 : 0x7f800000);
     if (lane == 0) { ws->cum_pad = __longlong_as_double(0xfff0000000000000ll); ws->op_pad = __longlong_as_double(0x7ff8000000000000ll); }
     __syncwarp();
     // warp-uniform values are broadcast from lane 0 so that the compiler can PROVE them uniform: loops and branches on them
@@ -552,11 +555,12 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 // First ordering of the lap (:506), from a guess: a lap moves few cars far, so the new rank is the old one
                 // plus the crossings counted against the two old neighbours on each side (times by OLD rank through W);
                 // like the run-reversal guess of the later passes it is VERIFIED below and recounted on a miss.
-                W[r] = cum;
+                const float key = (float)(cum - t_lead);
+                W[r] = key;
                 __syncwarp();
                 {
-                    const double a1 = W[r - 1], a2 = W[r - 2], b1 = W[r + 1], b2 = W[r + 2];
-                    r += (int)(b1 < cum) + (int)(b2 < cum) - (int)(cum < a1) - (int)(cum < a2);
+                    const float a1 = W[r - 1], a2 = W[r - 2], b1 = W[r + 1], b2 = W[r + 2];
+                    r += (int)(b1 < key) + (int)(b2 < key) - (int)(key < a1) - (int)(key < a2);
                 }
                 for (int pass = 0; pass < 3; pass++) {
                     S_inv[r] = lane;
