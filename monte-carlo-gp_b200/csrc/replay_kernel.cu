@@ -566,15 +566,16 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     S_inv[r] = lane;
                     S_cum[r] = cum;
                     S_op[r] = op_pub;
-                    const uint32_t cover = __reduce_or_sync(RFULL, 1u << r);
                     __syncwarp();
                     {
                         // r is a guess (window placement / every run of the last pass reversed: the re-written times descend
                         // by 0.1 s inside a run); it is THE order iff it is a permutation along which (time, grid slot)
-                        // increases strictly.
+                        // increases strictly.  ONE reduction checks both: every rank must be claimed by a lane that sits
+                        // strictly behind the car in the slot before it (two lanes on one rank leave another rank unclaimed).
                         const double c_prev = S_cum[r - 1];  // (rank 0 reads the -inf pad)
-                        const bool ok = c_prev < cum || (c_prev == cum && (int)S_inv[(r - 1) & 31] < lane);
-                        if (cover != RFULL || !__all_sync(RFULL, ok)) {
+                        const int l_prev = (int)S_inv[(r - 1) & 31];
+                        const bool ok = (c_prev < cum) | ((c_prev == cum) & (l_prev < lane));
+                        if (__reduce_or_sync(RFULL, ok ? (1u << r) : 0u) != RFULL) {
                             __syncwarp();
                             r = rank_set<NP>(cum, nmask, lane, S_p);  // ALL cars, retired ones included (Q5)
                             S_inv[r] = lane;
