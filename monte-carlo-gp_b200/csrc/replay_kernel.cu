@@ -589,6 +589,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     if (drs) delta += R.drs_delta;
                     const bool cond = !dnf && delta > R.ovt_delta;
                     const uint32_t CM = __reduce_or_sync(RFULL, cond ? (1u << r) : 0u);
+                    if (CM == 0u) { have_r = true; break; }  // nobody may attack: no draw is taken (:522-524), the pass changes nothing
                     if (py_rel + pc + __popc(CM) > py_ok) landed();  // (warp-uniform, rare: the lap outran what had landed at its start)
                     const double u = py_draw(__popc(CM & ((1u << r) - 1u)), cond);  // draws in sorted order :524
                     pc += __popc(CM);
