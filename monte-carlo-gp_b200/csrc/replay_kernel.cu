@@ -366,7 +366,7 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
         double t_lead = 0.0;  // time of the leading runner as of the last update_positions (warp-uniform)
         // Lanes without a car behave like cars parked behind the field for good: time +inf, retired from the start, rank ==
         // lane.  The rank-indexed exchanges below then need no `is_car` guard.
-        double cum = is_car ? 0.0 : __longlong_as_double(0x7ff0000000000000ll), last = 0.0, tbl = 0.0, ahead_last = 0.0;
+        double cum = is_car ? 0.0 : __longlong_as_double(0x7ff0000000000000ll), last = 0.0, ahead_last = 0.0;
 
         // _calculate_lap_time :313-332, strictly left to right
         auto lap_time = [&](int lap, double z) -> double {
@@ -399,7 +399,6 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 const double tp = S_cum[pr], lp = S_last[pr];
                 if (!dnf) {
                     pos_live = __popc(below);
-                    tbl = cum - t_lead;
                     if (lap <= 2 || drs_disabled || pos_live == 0) drs = false;
                     else drs = (cum - tp) < 1.0;
                     ahead_last = pos_live > 0 ? lp : 0.0;
@@ -473,7 +472,6 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     if (ev == 1) {  // _handle_red_flag :397-431
                         if (!dnf) {
                             cum = t0 + (double)pos_live * 0.1;
-                            tbl = cum - t0;
                             age = 0;
                             comp = track == 2 ? 4 : track == 1 ? 3 : rem > 30 ? 2 : rem > 15 ? 1 : 0;
                             used |= 1u << comp;
@@ -481,14 +479,12 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                     } else if (ev == 2) {  // _handle_safety_car :334-376 (lapped branch is dead code, Q6)
                         if (!dnf) {
                             cum = t0 + (double)pos_live * 0.5;
-                            tbl = cum - t0;
                             age = age - 1 > 0 ? age - 1 : 0;
                         }
                     } else {  // _handle_vsc :378-395
                         if (!dnf) {
                             const double gap = cum - t0;
                             cum = t0 + gap * 0.8;
-                            tbl = cum - t0;
                         }
                         const double r4 = py_draw(0, true); pc++;  // drawn only when somebody is still running :381-392
                         if (r4 < 0.3 && !dnf) age = age - 1 > 0 ? age - 1 : 0;
@@ -520,6 +516,9 @@ replay_race_kernel(const ReplayRace* __restrict__ race, unsigned long long n_sim
                 {   // (evaluated by every lane, kept by the runners: no divergent region around ~25 FP64 instructions)
                     const double clean = lap_time(lap, z);
                     const double dirty = clean + R.dirty_pen;
+                    // time_behind_leader (:552, :371, :389, :417) is always cumulative_time minus the leader's time as of the last
+                    // re-sort: recomputed here instead of carried across the lap (two registers)
+                    const double tbl = cum - t_lead;
                     const bool in_dirty_air = tbl > 0 && ahead_last > 0 && tbl < R.dirty_thr;
                     const double lt = in_dirty_air ? (dirty >= ahead_last ? dirty : ahead_last) : clean;
                     const double cum_new = cum + lt;
