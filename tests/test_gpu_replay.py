@@ -133,6 +133,24 @@ def test_replay_random_configurations(mcgp, oracle, block):
             assert np.array_equal(got["used"].cumsum(0), ref["draws"]), what
 
 
+@pytest.mark.parametrize("n,laps", [(20, 505), (32, 314), (21, 200), (1, 505), (20, 2)])
+def test_replay_extreme_sizes(mcgp, oracle, n, laps):
+    """The limits of the boundary: the longest races the pace table admits (505 laps up to 20 cars, 314 beyond), both
+    kernel instantiations, a one-car race, a two-lap race -- with events on ~20 % of the laps.  Bit-exact vs the oracle."""
+    wl = mcgp.workloads
+    D = [f"R{i:02d}" for i in range(n)]
+    cfg, _ = wl.workload("bahrain")
+    cfg.update(total_laps=laps, driver_teams={d: "Unknown" for d in D}, sc_probability=0.08, vsc_probability=0.1,
+               red_flag_probability=0.02)
+    mc = dict(grid_probs=wl.gaussian_grid_probs(D, spread=2.0), base_pace={d: 90 + 0.05 * i for i, d in enumerate(D)},
+              tire_deg={d: 0.03 for d in D}, driver_variance={d: 0.2 for d in D}, driver_dnf_rates={d: 0.0005 for d in D},
+              track_condition="dry")
+    ref, got = _replay(mcgp, oracle, cfg, mc, 11, 300, "SOFT", "MEDIUM")
+    assert np.array_equal(got["finish"], ref["finish"])
+    assert np.array_equal(got["times"].view(np.uint64), ref["times"].view(np.uint64))
+    assert np.array_equal(got["used"].cumsum(0), ref["draws"])
+
+
 def test_replay_tape_overrun_is_an_error(mcgp, oracle):
     cfg, mc, seed, _ = gc.get_case("small_grids")
     oparams = oracle.make_params(cfg, mc)
