@@ -8,6 +8,18 @@
 // bit-identical to CPython's.  lane == grid slot makes every "for car in cars" loop of the reference
 // (grid order) a lane-ordered prefix count (ballot + popc) over the tape cursors, and makes
 // the reference's stable-sort tie-break (list order) a plain (time, lane) comparison.
+// What is B200-native here and absent upstream (each verified bit-exact on the reference fixtures):
+//   * _sample_grid's per-position selection is a DISCRETE result: a 5-step warp scan of the raw items decides it, certified
+//     against the reference's serial arithmetic by an error bound (the serial evaluation, kept out of line, runs only where
+//     the draw is within 1e-12 of a boundary or the row is unusual);
+//   * every car keeps its rank; a lap's first ordering is the old rank plus the crossings against two neighbours on each
+//     side (float keys), an overtake pass's order the old one with each run of successes reversed -- guesses, VERIFIED in
+//     FP64 ((time, slot) strictly increasing along a permutation: one reduction) and recounted over all keys on a miss;
+//   * what a car needs from the car ahead (time, pace, last lap) sits in rank-indexed arrays with -inf / NaN pads in
+//     front of rank 0; lanes without a car are parked cars (time +inf, rank == lane): no guards in the exchanges;
+//   * the lap-loop tapes arrive through per-warp rings in shared memory, filled with cp.async a lap or more ahead;
+//   * sims are claimed dynamically; the warp index is broadcast from lane 0 so that every loop bound and branch of the sim /
+//     lap loops is provably uniform (no BRA.DIV guards around the warp collectives).
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
