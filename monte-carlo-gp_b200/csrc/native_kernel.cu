@@ -39,11 +39,15 @@
 
 namespace mcgp {
 
+// Block shape: 32 resident warps per SM (64 registers each) as ONE block of 32 warps.  A/B r2z on the headline launch:
+// 4 blocks of 8 warps 89.5 M, 2 blocks of 16 warps 90.0 M, 1 block of 32 warps 91.2 M races/s (one copy of the parameter
+// block and the pace tables per SM instead of four; a 505-lap race's 163 KB of pace tables still leaves all 32 warps
+// resident where four 8-warp blocks would have been cut to one).
 #ifndef MCGP_MIN_BLOCKS
-#define MCGP_MIN_BLOCKS 4  // resident 256-thread blocks per SM the register budget is tuned for
+#define MCGP_MIN_BLOCKS 1  // resident blocks per SM the register budget is tuned for
 #endif
 #ifndef MCGP_WARPS_PER_BLOCK
-#define MCGP_WARPS_PER_BLOCK 8
+#define MCGP_WARPS_PER_BLOCK 32
 #endif
 
 constexpr int kWarpsPerBlock = MCGP_WARPS_PER_BLOCK;
@@ -194,8 +198,8 @@ struct NativeOutputs {
 
 // kOut: 0 = count table only, 1 = + finish/times, 2 = + per-lap trace, 3 = + per-lap position histogram (the on-chip
 // reduction of the trace: BASELINE config 5's alternative output).  kWarps: warps per block -- the lap histogram lives
-// in shared memory (laps x n x n counters: 91 KB for 57 laps x 20 cars), so that variant runs ONE block of 32 warps
-// per SM where the others run four blocks of eight.
+// in shared memory (laps x n x n counters: 91 KB for 57 laps x 20 cars), so that variant always runs ONE block of 32
+// warps per SM (since round 2 the shape of every variant; a build with smaller blocks keeps the lap histogram at 32).
 template <int NV4, bool kExact, int kOut, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, (MCGP_MIN_BLOCKS * MCGP_WARPS_PER_BLOCK) / kWarps > 0 ? (MCGP_MIN_BLOCKS * MCGP_WARPS_PER_BLOCK) / kWarps : 1)
 native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict__ ptab, const int pt_rows, const int pt_stride,  // ptab: PacePair tables, two pairs per uint4
