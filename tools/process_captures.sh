@@ -4,13 +4,13 @@
 set -e
 tag=${1:-r2}
 g=gpurun_out
-python tools/ncu_summary.py $g/${tag}_native.ncu-rep ${tag}_native 2000000 --kernel native --note "headline kernel native_race_kernel<5,0,0,8>: python tests/checkers/ab_bench.py --sims 2000000 --reps 1 (third launch captured; no L2 fill before it)" > /dev/null
-python tools/ncu_summary.py $g/${tag}_native_trace.ncu-rep ${tag}_native_trace 1000000 --kernel native --note "trace variant <5,0,2,8>: ab_bench.py --sims 1000000 --reps 1 --mode trace" > /dev/null
+python tools/ncu_summary.py $g/${tag}_native.ncu-rep ${tag}_native 2000000 --kernel native --note "headline kernel native_race_kernel<5,0,0,32>: python tests/checkers/ab_bench.py --sims 2000000 --reps 1 (third launch captured; no L2 fill before it)" > /dev/null
+python tools/ncu_summary.py $g/${tag}_native_trace.ncu-rep ${tag}_native_trace 1000000 --kernel native --note "trace variant <5,0,2,32>: ab_bench.py --sims 1000000 --reps 1 --mode trace" > /dev/null
 python tools/ncu_summary.py $g/${tag}_native_laphist.ncu-rep ${tag}_native_laphist 2000000 --kernel native --note "lap-histogram variant <5,0,3,32>: ab_bench.py --sims 2000000 --reps 1 --mode laphist" > /dev/null
 python tools/ncu_summary.py $g/${tag}_replay.ncu-rep ${tag}_replay 40000 --kernel replay --note "replay_race_kernel<10>: tests/checkers/replay_bench.py --sims 40000 --reps 1 (synthetic worst-case-sized tapes)" > /dev/null
 tmp=$(mktemp -d)
 (cd $tmp && cuobjdump -xelf all $OLDPWD/monte-carlo-gp_b200/csrc/native_kernel.o > /dev/null && cuobjdump -xelf all $OLDPWD/monte-carlo-gp_b200/csrc/replay_kernel.o > /dev/null)
-python tools/sass_by_line.py $g/${tag}_native.ncu-rep $tmp/native_kernel.sm_100a.cubin native_race_kernelILi5ELb0ELi0ELi8 2000000 > profiles/${tag}_native_kernel_by_source_line.txt
+python tools/sass_by_line.py $g/${tag}_native.ncu-rep $tmp/native_kernel.sm_100a.cubin native_race_kernelILi5ELb0ELi0ELi32 2000000 > profiles/${tag}_native_kernel_by_source_line.txt
 python tools/sass_by_line.py $g/${tag}_replay.ncu-rep $tmp/replay_kernel.sm_100a.cubin replay_race_kernelILi10 40000 > profiles/${tag}_replay_kernel_by_source_line.txt
 rm -rf $tmp
 cp $g/${tag}_bench_reference_arm.json $g/${tag}_bench_launch_list.csv profiles/
