@@ -751,7 +751,14 @@ static cudaError_t launch_one(const LaunchArgs& a) {
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const long long resident = (long long)a.sm_count * per_sm;
+#ifdef MCGP_FLOOR_BLOCKS_PER_RACE
     long long bpr = resident / a.n_races;  // (never more blocks than fit at once: a waiting block could only start late)
+#else
+    // Blocks per race, rounded UP: with one block per SM, 148 SMs over a 24-race season would otherwise leave 4 SMs idle.
+    // The few blocks beyond what is resident start when the first ones retire -- by then the hopping blocks have claimed
+    // nearly everything, and what is left for a late block is its statically assigned first sim per warp.
+    long long bpr = (resident + a.n_races - 1) / a.n_races;
+#endif
     const long long need = (long long)((a.n_sims + kWarps - 1) / kWarps);
     if (bpr > need) bpr = need;
     if (bpr < 1) bpr = 1;
