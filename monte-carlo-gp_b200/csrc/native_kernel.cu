@@ -326,8 +326,14 @@ native_race_kernel(const NativeRace* __restrict__ races, const uint4* __restrict
                 float c = p;  // inclusive Hillis-Steele scan over lanes (the mirror replays this exact tree)
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
+#ifdef MCGP_SCAN_PLAIN
                     float v = __shfl_up_sync(FULL, c, d);
                     if (lane >= d) c = __fadd_rn(c, v);
+#else
+                    // the shuffle's own "source lane in range" predicate guards the add: no lane compare per step
+                    asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 v;\n\tshfl.sync.up.b32 v|q, %0, %1, 0, 0xffffffff;\n\t@q add.rn.f32 %0, %0, v;\n\t}"
+                                 : "+f"(c) : "r"(d));
+#endif
                 }
                 const float total = __shfl_sync(FULL, c, 31);
                 const float u = __shfl_sync(FULL, ug, pos);
